@@ -1,0 +1,27 @@
+// Library plumbing: error string, version, launch counter.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace davf {
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace davf
+
+extern "C" {
+const char* davf_last_error(void) { return davf::g_err; }
+int davf_version(void) { return 1; }
+int davf_device_sm(void) {
+  int dev = 0, major = 0, minor = 0;
+  DAVF_CUDA(cudaGetDevice(&dev));
+  DAVF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DAVF_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return major * 10 + minor;
+}
+int64_t davf_launch_count(void) { return davf::g_launches.load(); }
+}

@@ -1,0 +1,36 @@
+// davf_gemm: argument validation + dispatch (tcgen05 kernel by default, SIMT checker on request).
+#include "gemm_epilogue.cuh"
+
+namespace davf {
+static std::atomic<int> g_gemm_impl{0};
+}
+
+using namespace davf;
+
+extern "C" int davf_set_gemm_impl(int impl) {
+  DAVF_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: %d", impl);
+  g_gemm_impl.store(impl);
+  return DAVF_OK;
+}
+extern "C" int davf_get_gemm_impl(void) { return g_gemm_impl.load(); }
+
+extern "C" int davf_gemm(const davf_gemm_args* a, davf_stream_t s) {
+  DAVF_CHECK_ARG(a && a->a && a->b && a->out, "gemm: null pointer");
+  DAVF_CHECK_ARG(a->M >= 0 && a->N > 0 && a->K > 0, "gemm: bad sizes M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
+  if (a->M == 0) return DAVF_OK;
+  DAVF_CHECK_ARG(a->N % 8 == 0, "gemm: N=%lld must be a multiple of 8", (long long)a->N);
+  DAVF_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm: lda=%lld ldb=%lld must be multiples of 8 (16-byte TMA strides)", (long long)a->lda, (long long)a->ldb);
+  DAVF_CHECK_ARG(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)a->b & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "gemm: operands must be 16-byte aligned");
+  DAVF_CHECK_ARG(a->lda >= (a->a_kmajor ? a->K : a->M) && a->ldb >= (a->b_kmajor ? a->K : a->N), "gemm: leading dimension smaller than the row");
+  DAVF_CHECK_ARG(a->ldo % 4 == 0 && a->ldo >= a->N, "gemm: ldo=%lld", (long long)a->ldo);
+  DAVF_CHECK_ARG(a->act >= 0 && a->act <= 2, "gemm: act=%d", a->act);
+  DAVF_CHECK_ARG(a->act != DAVF_ACT_DGELU || a->aux_in, "gemm: DGELU needs aux_in");
+  DAVF_CHECK_ARG(!(a->aux_out || a->aux_in) || (a->ldaux % 4 == 0 && a->ldaux >= a->N), "gemm: ldaux=%lld", (long long)a->ldaux);
+  DAVF_CHECK_ARG(!a->res || (a->ldres % 4 == 0 && a->ldres >= a->N), "gemm: ldres=%lld", (long long)a->ldres);
+  DAVF_CHECK_ARG(!(a->accumulate && a->out_bf16), "gemm: accumulate needs an f32 output");
+  DAVF_CHECK_ARG(a->split_k <= 1 || a->accumulate, "gemm: split_k > 1 needs accumulate");
+  DAVF_CHECK_ARG(!a->accumulate || (a->act == DAVF_ACT_NONE && !a->res && !a->aux_out), "gemm: accumulate excludes act / res / aux_out");
+  DAVF_CHECK_ARG(a->g == 0 || (a->g > 0 && a->G >= a->g && a->off >= 0 && a->off + a->g <= a->G), "gemm: bad row window g=%d G=%d off=%d", a->g, a->G, a->off);
+  if (g_gemm_impl.load() == 1) return gemm_simt_launch(*a, as_stream(s));
+  return gemm_tc_launch(*a, as_stream(s));
+}

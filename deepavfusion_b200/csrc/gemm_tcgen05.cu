@@ -1,0 +1,410 @@
+// K1/K5/K9/K10: bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory, persistent over output tiles, warp
+// specialised:
+//     warp 0      TMA producer            (one elected lane)
+//     warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / commit)
+//     warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> fused epilogue -> global
+// Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a double-buffered TMEM accumulator
+// (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand layouts.  Both operands may be K-major (reduction dim contiguous in global memory) or
+// MN-major (row dim contiguous), which covers forward (K,K), dgrad (K,MN) and wgrad (MN,MN)
+// without any transposed copies in HBM:
+//   K-major  tile: [BLOCK rows][64 k] bf16, one TMA box {64,BLOCK}, canonical SW128 K-major layout
+//                  (SBO = 1024 B between 8-row groups, +32 B per UMMA_K step)
+//   MN-major tile: BLOCK/64 boxes {64 rows, 64 k}: [64 k][64 rows] each 8 KB, canonical SW128
+//                  MN-major layout (LBO = 8192 B between 64-row groups, SBO = 1024 B between
+//                  8-k groups, +2048 B per UMMA_K step)
+// Descriptor bit layouts follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction
+// descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+
+#include "gemm_epilogue.cuh"
+
+namespace davf {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr uint64_t kSpinLimit = 4000000000ull;   // ~2 s of SM clocks: trap instead of hanging the GPU
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
+      printf("davf gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 format: version = 1 at bit 46, layout type at [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);              // [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // [16,30) leading byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                                // [46,48) descriptor version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                                // [61,64) SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor for kind::f16, A/B = bf16, D = f32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // c_format  = F32
+         | (1u << 7)                     // a_format  = BF16
+         | (1u << 10)                    // b_format  = BF16
+         | ((uint32_t)a_mn_major << 15)  // a_major   (0 = K, 1 = MN)
+         | ((uint32_t)b_mn_major << 16)  // b_major
+         | ((uint32_t)(N >> 3) << 17)    // n_dim
+         | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+
+struct TileSched {
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  __device__ __forceinline__ int num_tiles() const { return m_tiles * n_tiles * splits; }
+  __device__ __forceinline__ void decode(int t, int& m_blk, int& n_blk, int& sp, int& kb0, int& kb1) const {
+    sp = t % splits;
+    const int mn = t / splits;
+    m_blk = mn % m_tiles;
+    n_blk = mn / m_tiles;
+    kb0 = sp * kb_per_split;
+    kb1 = min(kb_total, kb0 + kb_per_split);
+  }
+};
+
+template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               TileSched ts, EpiParams ep) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;            // two accumulator stages (power of two: 256 / 512)
+  constexpr uint32_t IDESC = make_idesc(BM, BN, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier addresses: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  const int num_tiles = ts.num_tiles();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk, sp, kb0, kb1;
+        ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (A_KMAJOR) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+          }
+          if (B_KMAJOR) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+        int m_blk, n_blk, sp, kb0, kb1;
+        ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = A_KMAJOR ? make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024)
+                                            : make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024);
+            const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
+                                            : make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+            umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
+    const int quad = warp & 3;
+    int local = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+      int m_blk, n_blk, sp, kb0, kb1;
+      ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float z[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_32x32b_x32(taddr, z);
+        epilogue_row<32>(ep, m, (int64_t)n_blk * BN + c * 32, z, sp == 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: TMA descriptor cache + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int64_t inner, outer, ld; int box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    h = h * 1000003u ^ (size_t)k.inner;
+    h = h * 1000003u ^ (size_t)k.outer;
+    h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)k.box_outer;
+    return h;
+  }
+};
+
+// 2-D bf16 tensor [outer][inner] with row pitch ld elements; box = {64, box_outer}, 128B swizzle,
+// out-of-bounds elements read as zero (M/N/K tails need no special casing in the kernel).
+static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, inner, outer, ld, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return DAVF_OK; }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DAVF_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld ld=%lld box=%d", (int)r, ptr, (long long)inner,
+              (long long)outer, (long long)ld, box_outer);
+    return DAVF_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return DAVF_OK;
+}
+
+template <int BN, int STAGES, bool AK, bool BKM>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 4) + 16 + 1024;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM>;
+  if (!attr_set) {
+    DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles = ts.m_tiles * ts.n_tiles * ts.splits;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kern<<<grid, kNumThreads, smem, st>>>(ta, tb, ts, ep);
+  DAVF_LAUNCH_OK();
+  return DAVF_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_major(const davf_gemm_args& a, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, cudaStream_t st) {
+  const EpiParams ep = make_epi(a);
+  if (a.a_kmajor && a.b_kmajor) return launch_cfg<BN, STAGES, true, true>(ta, tb, ts, ep, st);
+  if (a.a_kmajor && !a.b_kmajor) return launch_cfg<BN, STAGES, true, false>(ta, tb, ts, ep, st);
+  if (!a.a_kmajor && !a.b_kmajor) return launch_cfg<BN, STAGES, false, false>(ta, tb, ts, ep, st);
+  return launch_cfg<BN, STAGES, false, true>(ta, tb, ts, ep, st);
+}
+
+int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
+  // tile-N choice: 256-wide tiles halve the shared-memory operand traffic per FLOP; use them when
+  // the problem still yields at least ~one full wave of CTAs, otherwise 128 for parallelism.
+  const int64_t m_tiles = (a.M + BM - 1) / BM;
+  int bn = 128;
+  if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs) bn = 256;
+  const int64_t n_tiles = (a.N + bn - 1) / bn;
+  const int kb_total = (int)((a.K + BK - 1) / BK);
+  int splits = a.split_k;
+  if (splits <= 0) {   // auto: fill the machine when the caller allows atomic accumulation
+    splits = 1;
+    if (a.accumulate) {
+      const int64_t mn = m_tiles * n_tiles;
+      if (mn < kNumSMs) splits = (int)((kNumSMs + mn - 1) / mn);
+      if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+    }
+  }
+  if (splits > kb_total) splits = kb_total;
+  if (splits < 1) splits = 1;
+  int per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;          // no empty split
+  TileSched ts{(int)m_tiles, (int)n_tiles, splits, kb_total, per};
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
+  else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
+  if (rc) return rc;
+  if (a.b_kmajor) rc = get_tensor_map(a.b, a.K, a.N, a.ldb, bn, &tb);
+  else rc = get_tensor_map(a.b, a.N, a.K, a.ldb, BK, &tb);
+  if (rc) return rc;
+  if (bn == 256) return launch_major<256, 4>(a, ta, tb, ts, st);
+  return launch_major<128, 6>(a, ta, tb, ts, st);
+}
+
+}  // namespace davf

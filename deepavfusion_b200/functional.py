@@ -1,0 +1,404 @@
+"""Hand-ordered forward / backward of the hot-path building blocks.
+
+Each ``torch.autograd.Function`` below is one fused region of the model whose forward AND
+backward are explicit sequences of libdavf_sm100 kernel launches (``kernels.*``); autograd only
+stitches the regions together.  Parameter gradients never travel through autograd: wgrad GEMMs
+and bias / LayerNorm reductions accumulate straight into the flat gradient buffer
+(``ParamStore.grad``), so the Functions return ``None`` for every parameter.
+
+Precision contract (bf16 path of BASELINE.json; the reference runs the same graph under autocast):
+GEMM / attention operands bf16, accumulation f32; LayerNorm statistics, softmax, the residual
+stream, the loss and all parameter gradients f32.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from .params import ParamStore
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------
+# linear helpers (forward: K-major x K-major; dgrad: K x MN; wgrad: MN x MN -- no transposes)
+# --------------------------------------------------------------------------------------------
+def _w2d(t: Tensor, cols: Optional[Tuple[int, int]]) -> Tensor:
+    t = t.view(t.shape[0], -1)
+    return t if cols is None else t[:, cols[0]:cols[1]]
+
+
+def linear_fwd(st: ParamStore, x: Tensor, W: nn.Parameter, b: Optional[nn.Parameter], cols=None, **epi):
+    """y = x W[:, cols]^T (+ b) with the fused epilogue options of kernels.gemm."""
+    return K.gemm(x, _w2d(st.lowp(W), cols), True, True, bias=None if b is None else b.data, **epi)
+
+
+def linear_bwd(st: ParamStore, dy: Tensor, x: Tensor, W: nn.Parameter, b: Optional[nn.Parameter], cols=None,
+               need_dx: bool = True, **epi):
+    """Accumulates dW (+= dy^T x) and db (+= colsum dy) into the flat gradient buffer and returns
+    dx = dy W[:, cols] (with optional fused epilogue) or None."""
+    if W.requires_grad:
+        K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True)
+    if b is not None and b.requires_grad:
+        K.colsum_bf16(dy, st.grad(b))
+    if not need_dx:
+        return None
+    return K.gemm(dy, _w2d(st.lowp(W), cols), True, False, **epi)
+
+
+def _f32_rows(t: Tensor) -> Tensor:
+    return t.reshape(-1, t.shape[-1])
+
+
+# --------------------------------------------------------------------------------------------
+# a2  patch embed (+pos, kept rows only)        vits.py:91-100, timm PatchEmbed
+# --------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image: Tensor, ids_keep: Optional[Tensor], weight: nn.Parameter, m: SimpleNamespace):
+        st: ParamStore = m.store
+        B = image.shape[0]
+        p = m.patch
+        L = (image.shape[2] // p) * (image.shape[3] // p)
+        a = K.patch_rows(image, ids_keep, p)                       # [B*nK, C*p*p] bf16, kept patches only
+        nK = a.shape[0] // B
+        if ids_keep is None:
+            idx = torch.arange(L, device=image.device, dtype=torch.int64).repeat(B)
+        else:
+            idx = ids_keep.reshape(-1)
+        D = weight.shape[0]
+        x = linear_fwd(st, a, weight, m.bias, res=m.pos_embed.data.view(L, D), res_idx=idx, out_dtype=torch.float32)
+        ctx.m = m
+        ctx.save_for_backward(a)
+        return x.view(B, nK, D)
+
+    @staticmethod
+    def backward(ctx, dx: Tensor):
+        m = ctx.m
+        (a,) = ctx.saved_tensors
+        dxb = K.cast_rows_bf16(_f32_rows(dx.contiguous()))
+        linear_bwd(m.store, dxb, a, m.weight, m.bias, need_dx=False)
+        return None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a3  attention half of a timm Block:  y = x + proj(attn(qkv(LN(cat(xp, x)))))  on the live rows
+# --------------------------------------------------------------------------------------------
+class AttnBranchFn(torch.autograd.Function):
+    """xp = optional prefix rows (the fusion tokens of deepavfusion.py:104-105) that act as
+    keys / values only: their block outputs are discarded by the reference, so no query / proj /
+    MLP work is done for them."""
+
+    @staticmethod
+    def forward(ctx, xp: Optional[Tensor], x: Tensor, anchor: Tensor, m: SimpleNamespace):
+        st: ParamStore = m.store
+        B, n, D = x.shape
+        x = x.contiguous()
+        if xp is not None:
+            xp = xp.contiguous()
+            nP = xp.shape[1]
+            x0, x1 = xp, x
+        else:
+            nP = 0
+            x0, x1 = x, None
+        S = nP + n
+        H = m.heads
+        hd = D // H
+        xn, _, mean, rstd = K.layernorm_fwd(x0, x1, m.norm_w.data, m.norm_b.data, m.eps)
+        qkv = linear_fwd(st, xn, m.qkv_w, m.qkv_b)                                    # [B*S, 3D] bf16
+        q5 = qkv.view(B, S, 3, H, hd)
+        o, lse = K.attention_fwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], hd ** -0.5)  # [B,n,H,hd]
+        y = linear_fwd(st, o.view(B * n, D), m.proj_w, m.proj_b, res=x.view(B * n, D), out_dtype=torch.float32)
+        ctx.m, ctx.nP = m, nP
+        ctx.save_for_backward(x0, x1, mean, rstd, xn, qkv, o, lse)
+        return y.view(B, n, D)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        m, nP = ctx.m, ctx.nP
+        st: ParamStore = m.store
+        x0, x1, mean, rstd, xn, qkv, o, lse = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, n, D = dy.shape
+        S, H = nP + n, m.heads
+        hd = D // H
+        dyb = K.cast_rows_bf16(dy.view(B * n, D))
+        do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b)                # [B*n, D] bf16
+        dqkv = torch.empty_like(qkv)
+        d5 = dqkv.view(B, S, 3, H, hd)
+        if nP:
+            d5[:, :nP, 0].zero_()                                                     # dead queries
+        q5 = qkv.view(B, S, 3, H, hd)
+        K.attention_bwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], do.view(B, n, H, hd), lse, hd ** -0.5,
+                        d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2])
+        dxn = linear_bwd(st, dqkv, xn, m.qkv_w, m.qkv_b)                              # [B*S, D] bf16
+        gw, gb = st.grad(m.norm_w), st.grad(m.norm_b)
+        if nP:
+            dxp, dx = K.layernorm_bwd(x0, x1, m.norm_w.data, mean, rstd, dxn, None, None, dy, gw, gb,
+                                      need_dx0=ctx.needs_input_grad[0])
+        else:
+            dx, _ = K.layernorm_bwd(x0, None, m.norm_w.data, mean, rstd, dxn, None, dy, None, gw, gb)
+            dxp = None
+        return dxp, dx, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# MLP half of a timm Block / fusion block:  y = x + fc2(gelu(fc1(LN(x))))
+# --------------------------------------------------------------------------------------------
+class MlpBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, anchor: Tensor, m: SimpleNamespace):
+        st: ParamStore = m.store
+        x = x.contiguous()
+        D = x.shape[-1]
+        x2 = x.view(1, -1, D)
+        xn, _, mean, rstd = K.layernorm_fwd(x2, None, m.norm_w.data, m.norm_b.data, m.eps)
+        a, h = linear_fwd(st, xn, m.fc1_w, m.fc1_b, act=K.ACT_GELU, want_aux=True)   # a = gelu(h), h = pre-activation
+        y = linear_fwd(st, a, m.fc2_w, m.fc2_b, res=x2.view(-1, D), out_dtype=torch.float32)
+        ctx.m = m
+        ctx.save_for_backward(x2, mean, rstd, xn, h, a)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        m = ctx.m
+        st: ParamStore = m.store
+        x2, mean, rstd, xn, h, a = ctx.saved_tensors
+        dy = dy.contiguous()
+        D = dy.shape[-1]
+        dyb = K.cast_rows_bf16(dy.view(-1, D))
+        dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, act=K.ACT_DGELU, aux_in=h)      # dgrad fused with gelu'
+        dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b)
+        dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, dxn, None, dy.view(1, -1, D), None,
+                                st.grad(m.norm_w), st.grad(m.norm_b))
+        return dx.view(dy.shape), None, None
+
+
+# --------------------------------------------------------------------------------------------
+# final norms (vits.py:116 / deepavfusion.py:111-113): f32 in, f32 out
+# --------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, anchor: Tensor, m: SimpleNamespace):
+        x = x.contiguous()
+        D = x.shape[-1]
+        x2 = x.view(1, -1, D)
+        _, y, mean, rstd = K.layernorm_fwd(x2, None, m.norm_w.data, m.norm_b.data, m.eps, want_bf16=False, want_f32=True)
+        ctx.m = m
+        ctx.save_for_backward(x2, mean, rstd)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        m = ctx.m
+        st: ParamStore = m.store
+        x2, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, None, dy.view(-1, dy.shape[-1]), None, None,
+                                st.grad(m.norm_w), st.grad(m.norm_b))
+        return dx.view(dy.shape), None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a4  fusion-token attention of FusionBlock_FactorizedAVInteractions (fusion_blocks.py:235-283)
+#     out = LN_mm(xmm) + cat(proj(pair_attn), attn_v, attn_a)
+# --------------------------------------------------------------------------------------------
+class FusionAttnFn(torch.autograd.Function):
+    """The dense pair attention (:245-258) is evaluated in its exactly-equivalent factorised form
+    (SURVEY.md 7.1-2): k(xva_ij) = Wk1 v_i + Wk2 a_j + bk  =>  softmax over the 8x8 pairs is the
+    outer product of two 8-way softmaxes, and the value sum splits the same way; xva is never
+    materialised and the k / v projections shrink 8x."""
+
+    @staticmethod
+    def forward(ctx, xmm: Tensor, xv: Tensor, xa: Tensor, anchor: Tensor, m: SimpleNamespace):
+        st: ParamStore = m.store
+        xmm, xv, xa = xmm.contiguous(), xv.contiguous(), xa.contiguous()
+        B, F, D = xmm.shape
+        nmm, nv, na = m.tkns
+        H = m.heads
+        hd = D // H
+        qk = m.q_w.shape[0]
+        dq = qk // H
+        scale = hd ** -0.5                                                          # fusion_blocks.py:220-222
+        seg = [0, nmm, nmm + nv, F]
+        mm_b, mm_f, mean_m, rstd_m = K.layernorm_fwd(xmm, None, m.n_mm_w.data, m.n_mm_b.data, m.eps, True, True, seg)
+        m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
+        xv_n, _, mean_v, rstd_v = K.layernorm_fwd(xv, None, m.n_img_w.data, m.n_img_b.data, m.eps)
+        xa_n, _, mean_a, rstd_a = K.layernorm_fwd(xa, None, m.n_aud_w.data, m.n_aud_b.data, m.eps)
+        out = torch.empty(B * F, D, dtype=torch.float32, device=xmm.device)
+
+        def cross(tok, ctx_n, c, n_tok, off):
+            """CrossAttention (fusion_blocks.py:46-59) for n_tok aggregation tokens; writes
+            out[b, off:off+n_tok] = LN_mm(xmm)[b, off:...] + proj(.) and returns the bf16 proj output."""
+            Nc = ctx_n.shape[0] // B
+            q = linear_fwd(st, tok, c.q_w, c.q_b)                                   # [B*n_tok, D]
+            kv = linear_fwd(st, ctx_n, c.kv_w, c.kv_b)                              # [B*Nc, 2D]
+            kv5 = kv.view(B, Nc, 2, H, hd)
+            o, lse = K.attention_fwd(q.view(B, n_tok, H, hd), kv5[:, :, 0], kv5[:, :, 1], scale)
+            _, pr = linear_fwd(st, o.view(B * n_tok, D), c.proj_w, c.proj_b, want_aux=True, res=mm_f, out=out,
+                               window=(n_tok, F, off))
+            return q, kv, o, lse, pr
+
+        qv, kvv, ov, lse_v, pv = cross(mv, xv_n, m.attn_v, nv, nmm)
+        qa, kva, oa, lse_a, pa = cross(ma, xa_n, m.attn_a, na, nmm + nv)
+        # factorised pair attention
+        q2 = linear_fwd(st, m2, m.q_w, m.q_b)                                       # [B*nmm, qk]
+        k_v = linear_fwd(st, pv, m.k_w, m.k_b, cols=(0, D))                          # [B*nv, qk]  (bias on the v side)
+        v_v = linear_fwd(st, pv, m.v_w, m.v_b, cols=(0, D))                          # [B*nv, D]
+        k_a = linear_fwd(st, pa, m.k_w, None, cols=(D, 2 * D))
+        v_a = linear_fwd(st, pa, m.v_w, None, cols=(D, 2 * D))
+        q2v = q2.view(B, nmm, H, dq)
+        o2, lse2v = K.attention_fwd(q2v, k_v.view(B, nv, H, dq), v_v.view(B, nv, H, hd), scale)
+        _, lse2a = K.attention_fwd(q2v, k_a.view(B, na, H, dq), v_a.view(B, na, H, hd), scale, out=o2, accumulate=True)
+        o2 = o2.view(B * nmm, D)
+        linear_fwd(st, o2, m.proj_w, m.proj_b, res=mm_f, out=out, window=(nmm, F, 0))
+        ctx.m = m
+        ctx.save_for_backward(xmm, xv, xa, mean_m, rstd_m, mean_v, rstd_v, mean_a, rstd_a, mm_b, xv_n, xa_n,
+                              qv, kvv, ov, lse_v, pv, qa, kva, oa, lse_a, pa,
+                              q2, k_v, v_v, k_a, v_a, lse2v, lse2a, o2)
+        return out.view(B, F, D)
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        m = ctx.m
+        st: ParamStore = m.store
+        (xmm, xv, xa, mean_m, rstd_m, mean_v, rstd_v, mean_a, rstd_a, mm_b, xv_n, xa_n,
+         qv, kvv, ov, lse_v, pv, qa, kva, oa, lse_a, pa,
+         q2, k_v, v_v, k_a, v_a, lse2v, lse2a, o2) = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, F, D = dout.shape
+        nmm, nv, na = m.tkns
+        H = m.heads
+        hd = D // H
+        dq = m.q_w.shape[0] // H
+        scale = hd ** -0.5
+        d2 = dout.view(B * F, D)
+        m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
+        dseg = torch.empty_like(mm_b)                                               # d LN_mm(xmm), segment-major bf16
+        dm2, dmv, dma = dseg[:B * nmm], dseg[B * nmm:B * (nmm + nv)], dseg[B * (nmm + nv):]
+
+        # ---- pair attention ----
+        dr2 = K.cast_rows_bf16(d2, B * nmm, nmm, F, 0)
+        do2 = linear_bwd(st, dr2, o2, m.proj_w, m.proj_b).view(B, nmm, H, hd)
+        dq2 = torch.empty_like(q2)
+        dk_v, dv_v, dk_a, dv_a = torch.empty_like(k_v), torch.empty_like(v_v), torch.empty_like(k_a), torch.empty_like(v_a)
+        q2v = q2.view(B, nmm, H, dq)
+        K.attention_bwd(q2v, k_v.view(B, nv, H, dq), v_v.view(B, nv, H, hd), do2, lse2v, scale,
+                        dq2.view(B, nmm, H, dq), dk_v.view(B, nv, H, dq), dv_v.view(B, nv, H, hd))
+        K.attention_bwd(q2v, k_a.view(B, na, H, dq), v_a.view(B, na, H, hd), do2, lse2a, scale,
+                        dq2.view(B, nmm, H, dq), dk_a.view(B, na, H, dq), dv_a.view(B, na, H, hd), accumulate_dq=True)
+        linear_bwd(st, dq2, m2, m.q_w, m.q_b, out=dm2)
+
+        def pair_side(dk, dv, p_tok, cols, kb, vb, n_tok, off):
+            """d proj-output of one aggregation group = residual path + k path + v path."""
+            idx = (torch.arange(B, device=dout.device).view(B, 1) * F + off + torch.arange(n_tok, device=dout.device).view(1, n_tok)).reshape(-1)
+            t = linear_bwd(st, dk, p_tok, m.k_w, kb, cols=cols, res=d2, res_idx=idx, out_dtype=torch.float32)
+            return linear_bwd(st, dv, p_tok, m.v_w, vb, cols=cols, res=t, out_dtype=torch.bfloat16)
+
+        dpv = pair_side(dk_v, dv_v, pv, (0, D), m.k_b, m.v_b, nv, nmm)
+        dpa = pair_side(dk_a, dv_a, pa, (D, 2 * D), None, None, na, nmm + nv)
+
+        # ---- the two cross attentions ----
+        def cross_bwd(dp, tok, ctx_n, c, q, kv, o, lse, n_tok, d_tok_out):
+            Nc = ctx_n.shape[0] // B
+            do = linear_bwd(st, dp, o.view(B * n_tok, D), c.proj_w, c.proj_b).view(B, n_tok, H, hd)
+            dqc, dkv = torch.empty_like(q), torch.empty_like(kv)
+            kv5, dkv5 = kv.view(B, Nc, 2, H, hd), dkv.view(B, Nc, 2, H, hd)
+            K.attention_bwd(q.view(B, n_tok, H, hd), kv5[:, :, 0], kv5[:, :, 1], do, lse, scale,
+                            dqc.view(B, n_tok, H, hd), dkv5[:, :, 0], dkv5[:, :, 1])
+            linear_bwd(st, dqc, tok, c.q_w, c.q_b, out=d_tok_out)
+            return linear_bwd(st, dkv, ctx_n, c.kv_w, c.kv_b)                       # [B*Nc, D] bf16
+
+        dxv_n = cross_bwd(dpv, mv, xv_n, m.attn_v, qv, kvv, ov, lse_v, nv, dmv)
+        dxa_n = cross_bwd(dpa, ma, xa_n, m.attn_a, qa, kva, oa, lse_a, na, dma)
+
+        dxv, _ = K.layernorm_bwd(xv, None, m.n_img_w.data, mean_v, rstd_v, dxv_n, None, None, None,
+                                 st.grad(m.n_img_w), st.grad(m.n_img_b))
+        dxa, _ = K.layernorm_bwd(xa, None, m.n_aud_w.data, mean_a, rstd_a, dxa_n, None, None, None,
+                                 st.grad(m.n_aud_w), st.grad(m.n_aud_b))
+        seg = [0, nmm, nmm + nv, F]
+        dxmm, _ = K.layernorm_bwd(xmm, None, m.n_mm_w.data, mean_m, rstd_m, dseg, d2, None, None,
+                                  st.grad(m.n_mm_w), st.grad(m.n_mm_b), seg_start=seg)
+        return dxmm, dxv, dxa, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a6  decoder front: embed, mask tokens, unshuffle, +pos, cat fusion      avmae.py:158-169
+# --------------------------------------------------------------------------------------------
+class DecoderEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, xf: Tensor, ids_restore: Tensor, ids_keep: Tensor, anchor: Tensor, m: SimpleNamespace):
+        st: ParamStore = m.store
+        B, nK, D = x.shape
+        nF = xf.shape[1]
+        L = ids_restore.shape[1]
+        Dd = m.embed_w.shape[0]
+        xb = K.cast_rows_bf16(x.contiguous().view(B * nK, D))
+        xfb = K.cast_rows_bf16(xf.contiguous().view(B * nF, D))
+        e = linear_fwd(st, xb, m.embed_w, m.embed_b, out_dtype=torch.float32)
+        ef = linear_fwd(st, xfb, m.embed_w, m.embed_b, out_dtype=torch.float32)    # same Linear (avmae.py:158)
+        seq = K.decoder_assemble_fwd(e, ef, m.mask_token.data.view(Dd), m.pos_embed.data.view(L, Dd), ids_restore, nK, nF)
+        ctx.m, ctx.nF = m, nF
+        ctx.save_for_backward(xb, xfb, ids_restore, ids_keep)
+        return seq
+
+    @staticmethod
+    def backward(ctx, dseq: Tensor):
+        m, nF = ctx.m, ctx.nF
+        st: ParamStore = m.store
+        xb, xfb, ids_restore, ids_keep = ctx.saved_tensors
+        B, L = ids_restore.shape
+        nK = ids_keep.shape[1]
+        Dd = m.embed_w.shape[0]
+        D = xb.shape[1]
+        de, df = K.decoder_assemble_bwd(dseq.contiguous(), ids_keep, ids_restore, nF,
+                                        st.grad(m.mask_token).view(Dd), st.grad(m.pos_embed).view(L, Dd))
+        dx = linear_bwd(st, de, xb, m.embed_w, m.embed_b, out_dtype=torch.float32)
+        dxf = linear_bwd(st, df, xfb, m.embed_w, m.embed_b, out_dtype=torch.float32)
+        return dx.view(B, nK, D), dxf.view(B, nF, D), None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a6/a7  decoder head + loss: pred = Linear(LN(seq[:, nF:]));  loss = masked normalised MSE
+#        avmae.py:172,179 + :183-214
+# --------------------------------------------------------------------------------------------
+class PredLossFn(torch.autograd.Function):
+    """Returns (loss, pred).  ``pred`` is returned for inspection / logging and is NOT
+    differentiable (train.py:164 only consumes the two losses)."""
+
+    @staticmethod
+    def forward(ctx, seq: Tensor, img: Tensor, mask: Tensor, anchor: Tensor, m: SimpleNamespace):
+        st: ParamStore = m.store
+        seq = seq.contiguous()
+        B, S, Dd = seq.shape
+        L = mask.shape[1]
+        nF = S - L
+        xn, _, mean, rstd = K.layernorm_fwd(seq[:, nF:], None, m.norm_w.data, m.norm_b.data, m.eps)
+        pred = linear_fwd(st, xn, m.pred_w, m.pred_b, out_dtype=torch.float32)      # [B*L, P]
+        loss_sum = K.masked_mse_fwd(img, pred, mask, m.patch, L, 0, m.norm_pix)
+        count = B * (L - m.len_keep)                                                # == mask.sum(), avmae.py:197
+        ctx.m, ctx.count, ctx.nF = m, count, nF
+        ctx.save_for_backward(seq, img, mask, mean, rstd, xn, pred)
+        pred3 = pred.view(B, L, -1)
+        ctx.mark_non_differentiable(pred3)
+        return (loss_sum / count).reshape(()), pred3
+
+    @staticmethod
+    def backward(ctx, dloss: Tensor, _dpred):
+        m, count, nF = ctx.m, ctx.count, ctx.nF
+        st: ParamStore = m.store
+        seq, img, mask, mean, rstd, xn, pred = ctx.saved_tensors
+        B, S, Dd = seq.shape
+        L = S - nF
+        g = dloss.reshape(1).to(torch.float32).contiguous()
+        dpred = K.masked_mse_bwd(img, pred, mask, g, 1.0 / count, m.patch, L, 0, m.norm_pix)
+        dxn = linear_bwd(st, dpred, xn, m.pred_w, m.pred_b)
+        dseq = torch.empty_like(seq)
+        dseq[:, :nF].zero_()
+        K.layernorm_bwd(seq[:, nF:], None, m.norm_w.data, mean, rstd, dxn, None, None, None,
+                        st.grad(m.norm_w), st.grad(m.norm_b), dx0_out=dseq[:, nF:])
+        return dseq, None, None, None, None

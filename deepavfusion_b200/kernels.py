@@ -1,0 +1,368 @@
+"""Tensor-level wrappers over the C ABI (include/davf.h).
+
+PyTorch is used here for device memory and streams only: every wrapper checks dtypes / layouts,
+allocates outputs from the torch caching allocator, and launches the hand-written sm_100a kernels
+of libdavf_sm100.so on the current torch CUDA stream with raw device pointers.  There is no
+fallback: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import check
+
+Tensor = torch.Tensor
+ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t: Tensor, dtype, name: str, contiguous: bool = True) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the sm_100a kernels have no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor, got strides {t.stride()}")
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# K2 masking
+# --------------------------------------------------------------------------------------------
+def mask_rank(noise: Tensor, len_keep: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """noise f32 [B,L] -> (ids_restore i64 [B,L], ids_keep i64 [B,len_keep], mask f32 [B,L])."""
+    _need(noise, torch.float32, "noise")
+    B, L = noise.shape
+    ids_restore = torch.empty(B, L, dtype=torch.int64, device=noise.device)
+    ids_keep = torch.empty(B, len_keep, dtype=torch.int64, device=noise.device)
+    mask = torch.empty(B, L, dtype=torch.float32, device=noise.device)
+    check(_cabi.lib().davf_mask_rank(_ptr(noise), B, L, len_keep, _ptr(ids_restore), _ptr(ids_keep), _ptr(mask), _stream()), "davf_mask_rank")
+    return ids_restore, ids_keep, mask
+
+
+# --------------------------------------------------------------------------------------------
+# row kernels
+# --------------------------------------------------------------------------------------------
+def patch_rows(img: Tensor, ids_keep: Optional[Tensor], p: int) -> Tensor:
+    """img f32 [B,C,H,W] -> bf16 [B*nK, C*p*p] im2col rows (c,py,px order) of the kept patches."""
+    _need(img, torch.float32, "img")
+    B, Cc, H, W = img.shape
+    nK = (H // p) * (W // p) if ids_keep is None else ids_keep.shape[1]
+    if ids_keep is not None:
+        _need(ids_keep, torch.int64, "ids_keep")
+    out = torch.empty(B * nK, Cc * p * p, dtype=torch.bfloat16, device=img.device)
+    check(_cabi.lib().davf_patch_rows(_ptr(img), _ptr(ids_keep), _ptr(out), B, Cc, H, W, p, nK, _stream()), "davf_patch_rows")
+    return out
+
+
+def cast_rows_bf16(src: Tensor, M: Optional[int] = None, g: Optional[int] = None, G: Optional[int] = None, off: int = 0) -> Tensor:
+    """f32 rows -> bf16 [M, D]; output row m reads source row (m//g)*G + off + m%g."""
+    _need(src, torch.float32, "src")
+    D = src.shape[-1]
+    rows = src.numel() // D
+    if M is None:
+        M, g, G, off = rows, max(rows, 1), max(rows, 1), 0
+    out = torch.empty(M, D, dtype=torch.bfloat16, device=src.device)
+    check(_cabi.lib().davf_cast_rows_bf16(_ptr(src), _ptr(out), M, D, g, G, off, _stream()), "davf_cast_rows_bf16")
+    return out
+
+
+def cast_flat_bf16(src: Tensor, dst: Tensor) -> None:
+    _need(src, torch.float32, "src"); _need(dst, torch.bfloat16, "dst")
+    check(_cabi.lib().davf_cast_flat_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "davf_cast_flat_bf16")
+
+
+def colsum_bf16(x: Tensor, out: Tensor) -> None:
+    """out[n] += sum_m x[m, n]   (x bf16 [M,N] row-major view with stride(1) == 1)."""
+    _need(x, torch.bfloat16, "x", contiguous=False); _need(out, torch.float32, "out")
+    assert x.dim() == 2 and x.stride(1) == 1
+    check(_cabi.lib().davf_colsum_bf16(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _ptr(out), _stream()), "davf_colsum_bf16")
+
+
+def batchsum_f32(x: Tensor, off: int, g: int, out: Tensor, accumulate: bool) -> None:
+    """out[r, :] (+)= sum_b x[b, off + r, :]   (x f32 [B,G,D], out f32 [g,D])."""
+    _need(x, torch.float32, "x"); _need(out, torch.float32, "out")
+    B, G, D = x.shape
+    check(_cabi.lib().davf_batchsum_f32(_ptr(x), B, G, off, g, D, _ptr(out), int(accumulate), _stream()), "davf_batchsum_f32")
+
+
+# --------------------------------------------------------------------------------------------
+# K4 LayerNorm
+# --------------------------------------------------------------------------------------------
+def _bstride(x: Tensor) -> int:
+    """batch stride of a [B,n,D] tensor whose rows are dense (stride 0 = broadcast sample)."""
+    assert x.dim() == 3 and x.stride(2) == 1 and (x.shape[1] == 1 or x.stride(1) == x.shape[2]), x.stride()
+    return x.stride(0) if x.shape[0] > 1 else x.shape[1] * x.shape[2]
+
+
+def _segs(arr, seg_start):
+    n = 0
+    if seg_start is not None and len(seg_start) > 2:
+        n = len(seg_start) - 1
+        for k, v in enumerate(seg_start):
+            arr[k] = int(v)
+    return n
+
+
+def layernorm_fwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float,
+                  want_bf16: bool = True, want_f32: bool = False, seg_start: Optional[Sequence[int]] = None):
+    """LayerNorm over the rows of cat([x0, x1], dim=1).  Returns (y_bf16, y_f32, mean, rstd);
+    y_* are [B*(n0+n1), D] (bf16 rows are segment-major when seg_start has more than one segment)."""
+    _need(x0, torch.float32, "x0", contiguous=False)
+    B, n0, D = x0.shape
+    n1 = 0
+    if x1 is not None:
+        _need(x1, torch.float32, "x1", contiguous=False)
+        assert x1.shape[0] == B and x1.shape[2] == D
+        n1 = x1.shape[1]
+    rows = B * (n0 + n1)
+    dev = x0.device
+    y_bf16 = torch.empty(rows, D, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    y_f32 = torch.empty(rows, D, dtype=torch.float32, device=dev) if want_f32 else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev)
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    a = _cabi.LnFwdArgs()
+    a.x0, a.bs0, a.n0 = x0.data_ptr(), _bstride(x0), n0
+    a.x1, a.bs1, a.n1 = (x1.data_ptr() if x1 is not None else 0), (_bstride(x1) if x1 is not None else 0), n1
+    a.B, a.D, a.eps = B, D, float(eps)
+    a.gamma, a.beta = _need(gamma, torch.float32, "gamma").data_ptr(), _need(beta, torch.float32, "beta").data_ptr()
+    a.y_bf16 = y_bf16.data_ptr() if want_bf16 else 0
+    a.y_f32 = y_f32.data_ptr() if want_f32 else 0
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.nseg = _segs(a.seg_start, seg_start)
+    check(_cabi.lib().davf_layernorm_fwd(C.byref(a), _stream()), "davf_layernorm_fwd")
+    return y_bf16, y_f32, mean, rstd
+
+
+def layernorm_bwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
+                  dy_bf16: Optional[Tensor], dy_f32: Optional[Tensor],
+                  add0: Optional[Tensor], add1: Optional[Tensor], dgamma: Tensor, dbeta: Tensor,
+                  seg_start: Optional[Sequence[int]] = None, need_dx0: bool = True, need_dx1: bool = True,
+                  dx0_out: Optional[Tensor] = None):
+    """Returns (dx0 [B,n0,D] f32, dx1 [B,n1,D] f32 or None); dgamma / dbeta are accumulated in place.
+    ``dx0_out`` may be a [B,n0,D] view with a batch stride (rows dense) to write dx0 in place."""
+    B, n0, D = x0.shape
+    n1 = x1.shape[1] if x1 is not None else 0
+    dev = x0.device
+    if dx0_out is not None:
+        _need(dx0_out, torch.float32, "dx0_out", contiguous=False)
+        assert add0 is None or dx0_out.is_contiguous()
+        dx0 = dx0_out
+    else:
+        dx0 = torch.empty(B, n0, D, dtype=torch.float32, device=dev) if need_dx0 else None
+    dx1 = torch.empty(B, n1, D, dtype=torch.float32, device=dev) if (x1 is not None and need_dx1) else None
+    a = _cabi.LnBwdArgs()
+    a.x0, a.bs0, a.n0 = x0.data_ptr(), _bstride(x0), n0
+    a.x1, a.bs1, a.n1 = (x1.data_ptr() if x1 is not None else 0), (_bstride(x1) if x1 is not None else 0), n1
+    a.B, a.D = B, D
+    a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dy_bf16 = _need(dy_bf16, torch.bfloat16, "dy_bf16").data_ptr() if dy_bf16 is not None else 0
+    a.dy_f32 = _need(dy_f32, torch.float32, "dy_f32").data_ptr() if dy_f32 is not None else 0
+    a.dx0, a.dbs0 = (dx0.data_ptr() if dx0 is not None else 0), (_bstride(dx0) if dx0 is not None else n0 * D)
+    a.add0 = _need(add0, torch.float32, "add0").data_ptr() if add0 is not None else 0
+    a.dx1, a.dbs1 = (dx1.data_ptr() if dx1 is not None else 0), n1 * D
+    a.add1 = _need(add1, torch.float32, "add1").data_ptr() if add1 is not None else 0
+    a.dgamma, a.dbeta = _need(dgamma, torch.float32, "dgamma").data_ptr(), _need(dbeta, torch.float32, "dbeta").data_ptr()
+    a.nseg = _segs(a.seg_start, seg_start)
+    check(_cabi.lib().davf_layernorm_bwd(C.byref(a), _stream()), "davf_layernorm_bwd")
+    return dx0, dx1
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------
+def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
+         bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
+         res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
+         out: Optional[Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False,
+         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0):
+    """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of davf.h.
+
+    ``a`` / ``b`` are the STORED 2-D bf16 matrices (row-major views, stride(1) == 1):
+    K-major operand: stored [rows, K]; MN-major operand: stored [K, rows].
+    ``window`` = (g, G, off): output (and residual) row of m is (m//g)*G + off + m%g; ``out`` must
+    then be given.  Returns ``out`` or ``(out, aux)`` when ``want_aux``."""
+    _need(a, torch.bfloat16, "a", contiguous=False); _need(b, torch.bfloat16, "b", contiguous=False)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if a_kmajor:
+        M, K = a.shape
+    else:
+        K, M = a.shape
+    if b_kmajor:
+        N, Kb = b.shape
+    else:
+        Kb, N = b.shape
+    assert K == Kb, f"gemm: reduction mismatch {K} vs {Kb}"
+    dev = a.device
+    if out is None:
+        assert window is None and not accumulate
+        out = torch.empty(M, N, dtype=out_dtype, device=dev)
+    assert out.stride(-1) == 1
+    ga = _cabi.GemmArgs()
+    ga.a, ga.lda, ga.a_kmajor = a.data_ptr(), a.stride(0), int(a_kmajor)
+    ga.b, ga.ldb, ga.b_kmajor = b.data_ptr(), b.stride(0), int(b_kmajor)
+    ga.M, ga.N, ga.K = M, N, K
+    ga.bias = _need(bias, torch.float32, "bias").data_ptr() if bias is not None else 0
+    ga.act = act
+    aux = None
+    if want_aux:
+        aux = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        ga.aux_out, ga.ldaux = aux.data_ptr(), N
+    if aux_in is not None:
+        _need(aux_in, torch.bfloat16, "aux_in")
+        ga.aux_in, ga.ldaux = aux_in.data_ptr(), aux_in.shape[-1]
+    if res is not None:
+        _need(res, torch.float32, "res", contiguous=False)
+        assert res.stride(-1) == 1
+        ga.res, ga.ldres = res.data_ptr(), res.stride(-2)
+    if res_idx is not None:
+        ga.res_idx = _need(res_idx, torch.int64, "res_idx").data_ptr()
+    ga.out, ga.ldo = out.data_ptr(), out.stride(-2)
+    ga.out_bf16 = int(out.dtype == torch.bfloat16)
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    ga.accumulate = int(accumulate)
+    if window is not None:
+        ga.g, ga.G, ga.off = window
+    ga.split_k = split_k
+    check(_cabi.lib().davf_gemm(C.byref(ga), _stream()), "davf_gemm")
+    return (out, aux) if want_aux else out
+
+
+# --------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------
+def _bhs(t: Tensor, name: str):
+    """[B, N, H, d] bf16 view with unit stride on d and head stride d -> (ptr, batch stride, row stride)."""
+    _need(t, torch.bfloat16, name, contiguous=False)
+    assert t.dim() == 4 and t.stride(3) == 1 and (t.shape[2] == 1 or t.stride(2) == t.shape[3]), (name, t.shape, t.stride())
+    return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float, out: Optional[Tensor] = None, accumulate: bool = False):
+    """q [B,Nq,H,dqk], k [B,Nk,H,dqk], v [B,Nk,H,dv] strided bf16 views -> (o [B,Nq,H,dv] bf16, lse f32 [B,H,Nq])."""
+    B, Nq, H, dqk = q.shape
+    Nk, dv = k.shape[1], v.shape[3]
+    if out is None:
+        out = torch.empty(B, Nq, H, dv, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+    a = _cabi.AttnFwdArgs()
+    a.q, a.q_bs, a.q_rs = _bhs(q, "q")
+    a.k, a.k_bs, a.k_rs = _bhs(k, "k")
+    a.v, a.v_bs, a.v_rs = _bhs(v, "v")
+    a.o, a.o_bs, a.o_rs = _bhs(out, "o")
+    a.lse = lse.data_ptr()
+    a.B, a.H, a.Nq, a.Nk, a.dqk, a.dv = B, H, Nq, Nk, dqk, dv
+    a.scale, a.accumulate = float(scale), int(accumulate)
+    check(_cabi.lib().davf_attention_fwd(C.byref(a), _stream()), "davf_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, lse: Tensor, scale: float,
+                  dq: Tensor, dk: Tensor, dv: Tensor, accumulate_dq: bool = False) -> None:
+    """Writes dq / dk / dv (strided bf16 views shaped like q / k / v)."""
+    B, Nq, H, dqk = q.shape
+    Nk, dvd = k.shape[1], v.shape[3]
+    a = _cabi.AttnBwdArgs()
+    a.q, a.q_bs, a.q_rs = _bhs(q, "q")
+    a.k, a.k_bs, a.k_rs = _bhs(k, "k")
+    a.v, a.v_bs, a.v_rs = _bhs(v, "v")
+    a.d_o, a.do_bs, a.do_rs = _bhs(d_o, "d_o")
+    a.lse = _need(lse, torch.float32, "lse").data_ptr()
+    a.dq, a.dq_bs, a.dq_rs = _bhs(dq, "dq")
+    a.dk, a.dk_bs, a.dk_rs = _bhs(dk, "dk")
+    a.dv_, a.dv_bs, a.dv_rs = _bhs(dv, "dv")
+    a.B, a.H, a.Nq, a.Nk, a.dqk, a.dv = B, H, Nq, Nk, dqk, dvd
+    a.scale, a.accumulate_dq = float(scale), int(accumulate_dq)
+    check(_cabi.lib().davf_attention_bwd(C.byref(a), _stream()), "davf_attention_bwd")
+
+
+# --------------------------------------------------------------------------------------------
+# decoder assembly
+# --------------------------------------------------------------------------------------------
+def decoder_assemble_fwd(e: Tensor, ef: Tensor, mask_token: Tensor, pos: Tensor, ids_restore: Tensor, nK: int, nF: int) -> Tensor:
+    """e f32 [B*nK,D], ef f32 [B*nF,D], mask_token f32 [D], pos f32 [L,D], ids_restore i64 [B,L] -> seq f32 [B,nF+L,D]."""
+    B, L = ids_restore.shape
+    D = e.shape[-1]
+    for t, n in ((e, "e"), (ef, "ef"), (mask_token, "mask_token"), (pos, "pos")):
+        _need(t, torch.float32, n)
+    _need(ids_restore, torch.int64, "ids_restore")
+    seq = torch.empty(B, nF + L, D, dtype=torch.float32, device=e.device)
+    check(_cabi.lib().davf_decoder_assemble_fwd(_ptr(e), _ptr(ef), _ptr(mask_token), _ptr(pos), _ptr(ids_restore), _ptr(seq),
+                                               B, nK, nF, L, D, _stream()), "davf_decoder_assemble_fwd")
+    return seq
+
+
+def decoder_assemble_bwd(dseq: Tensor, ids_keep: Tensor, ids_restore: Tensor, nF: int, dmask_token: Tensor, dpos: Tensor):
+    """dseq f32 [B,nF+L,D] -> (de bf16 [B*nK,D], def bf16 [B*nF,D]); dmask_token [D] / dpos [L,D] accumulated."""
+    _need(dseq, torch.float32, "dseq")
+    B, S, D = dseq.shape
+    L, nK = S - nF, ids_keep.shape[1]
+    de = torch.empty(B * nK, D, dtype=torch.bfloat16, device=dseq.device)
+    df = torch.empty(B * nF, D, dtype=torch.bfloat16, device=dseq.device)
+    check(_cabi.lib().davf_decoder_assemble_bwd(_ptr(dseq), _ptr(_need(ids_keep, torch.int64, "ids_keep")),
+                                               _ptr(_need(ids_restore, torch.int64, "ids_restore")), _ptr(de), _ptr(df),
+                                               _ptr(_need(dmask_token, torch.float32, "dmask_token")), _ptr(_need(dpos, torch.float32, "dpos")),
+                                               B, nK, nF, L, D, _stream()), "davf_decoder_assemble_bwd")
+    return de, df
+
+
+# --------------------------------------------------------------------------------------------
+# loss
+# --------------------------------------------------------------------------------------------
+def masked_mse_fwd(img: Tensor, pred: Tensor, mask: Tensor, p: int, pred_G: int, pred_off: int, norm_pix: bool) -> Tensor:
+    """Returns loss_sum f32 [1] = sum over masked patches of mean((pred - target)^2)."""
+    _need(img, torch.float32, "img"); _need(pred, torch.float32, "pred"); _need(mask, torch.float32, "mask")
+    B, Cc, H, W = img.shape
+    out = torch.zeros(1, dtype=torch.float32, device=img.device)
+    check(_cabi.lib().davf_masked_mse_fwd(_ptr(img), _ptr(pred), _ptr(mask), _ptr(out), B, Cc, H, W, p, pred_G, pred_off,
+                                         int(norm_pix), _stream()), "davf_masked_mse_fwd")
+    return out
+
+
+def masked_mse_bwd(img: Tensor, pred: Tensor, mask: Tensor, gscale: Tensor, inv_count: float, p: int, pred_G: int,
+                   pred_off: int, norm_pix: bool) -> Tensor:
+    """Returns dpred bf16 [B*L, P]."""
+    B, Cc, H, W = img.shape
+    L = (H // p) * (W // p)
+    dpred = torch.empty(B * L, p * p * Cc, dtype=torch.bfloat16, device=img.device)
+    check(_cabi.lib().davf_masked_mse_bwd(_ptr(img), _ptr(pred), _ptr(mask), _ptr(_need(gscale, torch.float32, "gscale")),
+                                         float(inv_count), _ptr(dpred), B, Cc, H, W, p, pred_G, pred_off, int(norm_pix), _stream()),
+          "davf_masked_mse_bwd")
+    return dpred
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer
+# --------------------------------------------------------------------------------------------
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p_bf16: Optional[Tensor], seg_end: Sequence[int],
+               hp: Tensor, scal: Tensor, beta1: float, beta2: float, eps: float, zero_grad: bool) -> None:
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (hp, "hp"), (scal, "scal")):
+        _need(t, torch.float32, n)
+    arr = (C.c_int64 * len(seg_end))(*[int(x) for x in seg_end])
+    check(_cabi.lib().davf_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), C.cast(arr, C.c_void_p),
+                                     _ptr(hp), len(seg_end), _ptr(scal), beta1, beta2, eps, int(zero_grad), _stream()),
+          "davf_adamw_step")
+
+
+def sumsq_f32(g: Tensor, out: Tensor) -> None:
+    check(_cabi.lib().davf_sumsq_f32(_ptr(_need(g, torch.float32, "g")), g.numel(), _ptr(_need(out, torch.float32, "out")), _stream()),
+          "davf_sumsq_f32")
+
+
+def launch_count() -> int:
+    return int(_cabi.lib().davf_launch_count())
+
+
+def set_gemm_impl(impl: int) -> None:
+    check(_cabi.lib().davf_set_gemm_impl(impl), "davf_set_gemm_impl")

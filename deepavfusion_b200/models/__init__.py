@@ -1,0 +1,2 @@
+from .deepavfusion import DeepAVFusion  # noqa: F401
+from .avmae import AVMAE  # noqa: F401

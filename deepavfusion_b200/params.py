@@ -1,0 +1,164 @@
+"""Flat parameter / gradient / bf16-shadow storage laid out for 180 GB of HBM.
+
+All parameters of the top-level module become views into ONE f32 buffer (so a single fused
+AdamW launch and a handful of large gradient buckets cover the model), gradients are views into
+one f32 buffer that the wgrad GEMMs accumulate into directly (no autograd ``AccumulateGrad``
+copies; the ``+=`` also implements gradient accumulation over micro-steps, misc.py:144-148), and
+every parameter has a bf16 shadow at the same offset that the tensor-core kernels read (what
+autocast re-casts on every forward in the reference).
+
+Parameters stay ordinary ``nn.Parameter`` objects: ``state_dict()``, ``named_parameters()``,
+``load_state_dict(strict=True)``, ``torch.optim`` and ``param.grad`` consumers (misc.py:151-163)
+keep working.  Order inside the buffers is by optimizer group class so that every param group of
+util/lr_sched.py:77-92 is a union of contiguous segments:
+    (other | encoder.image | encoder.audio) x (no_decay | decay).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+from torch import nn
+
+ALIGN = 64          # elements; keeps every tensor 256-byte (f32) / 128-byte (bf16) aligned for TMA
+
+
+def group_class(name: str, p: torch.Tensor) -> int:
+    """0..5 = region*2 + decay.  no_decay rule = timm param_groups_weight_decay (ndim <= 1 or
+    '.bias') plus train.py:88 ('bias' or 'norm' in the name)."""
+    region = 1 if name.startswith("encoder.image.") or name.startswith("image.") else \
+        2 if name.startswith("encoder.audio.") or name.startswith("audio.") else 0
+    no_decay = p.ndim <= 1 or name.endswith(".bias") or "bias" in name or "norm" in name
+    return region * 2 + (0 if no_decay else 1)
+
+
+class ParamStore:
+    def __init__(self, module: nn.Module):
+        named = [(n, p) for n, p in module.named_parameters()]
+        assert named, "module has no parameters"
+        dev = named[0][1].device
+        order = sorted(range(len(named)), key=lambda i: (group_class(*named[i]), i))
+        self.names: List[str] = []
+        self.params: List[nn.Parameter] = []
+        self.offsets: List[int] = []
+        self.classes: List[int] = []
+        off = 0
+        for i in order:
+            n, p = named[i]
+            assert p.dtype == torch.float32, f"{n}: master parameters must be f32"
+            self.names.append(n); self.params.append(p); self.offsets.append(off); self.classes.append(group_class(n, p))
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.device = dev
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_lp = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self._index: Dict[int, int] = {}
+        self._lp: List[torch.Tensor] = []
+        self._g: List[torch.Tensor] = []
+        with torch.no_grad():
+            for k, (p, o) in enumerate(zip(self.params, self.offsets)):
+                view = self.flat_p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self._index[id(p)] = k
+                self._lp.append(self.flat_lp[o:o + p.numel()].view(p.shape))
+                self._g.append(self.flat_g[o:o + p.numel()].view(p.shape))
+                if p.requires_grad:
+                    p.grad = self._g[k]
+        self._versions = None
+        self._depth = 0
+        self.refresh_lowp(force=True)
+
+    # -- re-entrancy: nested module forwards skip the per-forward checks ------------------------
+    def __enter__(self):
+        self._depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        self._depth -= 1
+        return False
+
+    # -- identity ---------------------------------------------------------------------------
+    def owns(self, module: nn.Module) -> bool:
+        """True while every parameter still aliases the flat buffer (``.to()`` / ``.cuda()`` /
+        re-assignment of ``.data`` break the aliasing and require a rebuild)."""
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != self.flat_p.data_ptr() + 4 * o:
+                return False
+        return True
+
+    def covers(self, module: nn.Module) -> bool:
+        """Cheap per-forward check: a sample of ``module``'s parameters is in this store and still
+        aliases the flat buffer."""
+        ps = list(module.parameters())
+        for p in (ps[0], ps[len(ps) // 2], ps[-1]):
+            k = self._index.get(id(p))
+            if k is None or p.data_ptr() != self.flat_p.data_ptr() + 4 * self.offsets[k]:
+                return False
+        return True
+
+    # -- bf16 shadows -------------------------------------------------------------------------
+    def _version_key(self):
+        return tuple(p._version for p in self.params)
+
+    def refresh_lowp(self, force: bool = False) -> bool:
+        """Re-cast f32 -> bf16 if any parameter was modified in place since the last cast
+        (optimizer step, load_state_dict, init).  One launch over the flat buffer."""
+        key = self._version_key()
+        if not force and key == self._versions:
+            return False
+        from . import kernels as K
+        K.cast_flat_bf16(self.flat_p, self.flat_lp)
+        self._versions = key
+        return True
+
+    def mark_lowp_fresh(self) -> None:
+        """Called by the fused optimizer, which writes the bf16 shadows itself."""
+        self._versions = self._version_key()
+
+    def lowp(self, p: nn.Parameter) -> torch.Tensor:
+        return self._lp[self._index[id(p)]]
+
+    # -- gradients ------------------------------------------------------------------------------
+    def _attached(self, p: nn.Parameter, k: int) -> bool:
+        g = p.grad
+        return g is not None and g.data_ptr() == self._g[k].data_ptr() and g.dtype == torch.float32
+
+    def ensure_grads(self, force: bool = False) -> None:
+        """Re-attach ``.grad`` views after a ``zero_grad(set_to_none=True)`` by a stock optimizer
+        (torch's default): one flat memset instead of ~900 small ones."""
+        first = next((p for p in self.params if p.requires_grad), None)
+        if first is None or (not force and self._attached(first, self._index[id(first)])):
+            return
+        if all(p.grad is None for p in self.params if p.requires_grad):
+            self.flat_g.zero_()
+        for k, p in enumerate(self.params):
+            if p.requires_grad:
+                if p.grad is not None and not self._attached(p, k):
+                    self._g[k].copy_(p.grad)
+                p.grad = self._g[k]
+
+    def grad(self, p: nn.Parameter) -> torch.Tensor:
+        k = self._index[id(p)]
+        if not self._attached(p, k):
+            self.ensure_grads(force=True)
+        return self._g[k]
+
+    def zero_grad(self) -> None:
+        self.flat_g.zero_()
+        for k, p in enumerate(self.params):
+            if p.requires_grad and not self._attached(p, k):
+                p.grad = self._g[k]
+
+    # -- optimizer segments ----------------------------------------------------------------------
+    def segments(self) -> List[Tuple[int, int, int]]:
+        """[(class, begin, end)] contiguous element ranges per group class."""
+        segs: List[Tuple[int, int, int]] = []
+        for k, c in enumerate(self.classes):
+            end = self.offsets[k + 1] if k + 1 < len(self.offsets) else self.numel
+            if segs and segs[-1][0] == c:
+                segs[-1] = (c, segs[-1][1], end)
+            else:
+                segs.append((c, self.offsets[k], end))
+        return segs

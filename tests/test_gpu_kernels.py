@@ -1,0 +1,269 @@
+"""-m gpu: every CUDA kernel of libdavf_sm100.so against its torch emulation (tests/cpu_kernels.py,
+which the CPU suite in turn checks against the oracle) on the same seeded inputs, through the C ABI."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import cpu_kernels as E
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def K():
+    import deepavfusion_b200.kernels as K
+    assert K._cabi.lib().davf_device_sm() >= 100
+    return K
+
+
+def rnd(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def close(a, b, rtol, atol, what=""):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    assert bool((err <= tol).all()), f"{what}: max err {float(err.max()):.3e} (rel-L2 {float((a-b).norm()/(b.norm()+1e-30)):.3e})"
+
+
+# ---------------------------------------------------------------- masking (bit exact)
+@pytest.mark.parametrize("B,L,ratio", [(64, 196, 0.75), (64, 96, 0.8), (3, 8, 0.8), (1, 1024, 0.5)])
+def test_mask_rank_bit_exact(K, B, L, ratio):
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    noise = torch.rand(B, L, generator=g)
+    if L >= 96:                               # force exact ties, the unspecified-order case
+        noise[:, 5] = noise[:, 77]
+        noise[0, :16] = 0.25
+    keep = int(L * (1 - ratio))
+    r, k, m = K.mask_rank(noise.cuda(), keep)
+    er, ek, em = E.mask_rank(noise, keep)
+    assert torch.equal(r.cpu(), er) and torch.equal(k.cpu(), ek) and torch.equal(m.cpu(), em)
+    assert float(m.sum()) == B * (L - keep)
+    assert torch.equal(torch.gather(r.cpu(), 1, ek), torch.arange(keep).expand(B, -1))
+
+
+def test_mask_rank_golden(K):
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "mask_ties.npz"))
+    r, k, m = K.mask_rank(torch.from_numpy(d["noise"]).cuda(), d["ids_keep"].shape[1])
+    assert (r.cpu().numpy() == d["ids_restore"]).all() and (k.cpu().numpy() == d["ids_keep"]).all() and (m.cpu().numpy() == d["mask"]).all()
+
+
+# ---------------------------------------------------------------- row kernels
+@pytest.mark.parametrize("C,H,W,masked", [(3, 224, 224, True), (1, 128, 192, True), (3, 64, 64, False)])
+def test_patch_rows(K, C, H, W, masked):
+    B, p = 4, 16
+    img = rnd(B, C, H, W, seed=1)
+    L = (H // p) * (W // p)
+    ids = None
+    if masked:
+        ids = torch.stack([torch.randperm(L, generator=torch.Generator().manual_seed(i))[: max(1, L // 4)] for i in range(B)]).cuda()
+    out = K.patch_rows(img, ids, p)
+    ref = E.patch_rows(img.cpu(), None if ids is None else ids.cpu(), p)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_cast_colsum_batchsum(K):
+    x = rnd(6 * 32, 768, seed=2)
+    assert torch.equal(K.cast_rows_bf16(x).cpu(), x.cpu().to(bf16))
+    w = K.cast_rows_bf16(x, 6 * 8, 8, 32, 16)
+    assert torch.equal(w.cpu(), E.cast_rows_bf16(x.cpu(), 6 * 8, 8, 32, 16))
+    xb = rnd(3136, 2304, seed=3, dtype=bf16)
+    out = torch.zeros(2304, device="cuda")
+    K.colsum_bf16(xb, out)
+    close(out, xb.float().sum(0), 1e-4, 1e-3, "colsum")
+    sl = xb[:, 768:1536]
+    out2 = torch.ones(768, device="cuda")
+    K.colsum_bf16(sl, out2)
+    close(out2, 1 + sl.float().sum(0), 1e-4, 1e-3, "colsum strided")
+    x3 = rnd(5, 32, 512, seed=4)
+    o = torch.ones(8, 512, device="cuda")
+    K.batchsum_f32(x3, 16, 8, o, True)
+    close(o, 1 + x3[:, 16:24].sum(0), 1e-5, 1e-5, "batchsum")
+
+
+# ---------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("D,n0,n1,B,seg", [(768, 32, 49, 4, None), (512, 228, 0, 3, None), (768, 32, 0, 5, [0, 16, 24, 32]), (128, 7, 3, 2, None)])
+def test_layernorm_fwd_bwd(K, D, n0, n1, B, seg):
+    x0 = rnd(B, n0, D, seed=5) * 2 + 0.3
+    x1 = rnd(B, n1, D, seed=6) if n1 else None
+    gam, bet = rnd(D, seed=7) * 0.1 + 1, rnd(D, seed=8) * 0.1
+    yb, yf, mean, rstd = K.layernorm_fwd(x0, x1, gam, bet, 1e-6, True, True, seg)
+    eyb, eyf, emean, erstd = E.layernorm_fwd(x0.cpu(), None if x1 is None else x1.cpu(), gam.cpu(), bet.cpu(), 1e-6, True, True, seg)
+    close(yf, eyf, 1e-4, 1e-4, "ln y_f32"); close(mean, emean, 1e-4, 1e-5, "mean"); close(rstd, erstd, 1e-4, 1e-5, "rstd")
+    close(yb, eyb, 1e-2, 1e-2, "ln y_bf16")
+    rows = B * (n0 + n1)
+    dyb = rnd(rows, D, seed=9, dtype=bf16)
+    dyf = rnd(rows, D, seed=10)
+    add0 = rnd(B, n0, D, seed=11)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx0, dx1 = K.layernorm_bwd(x0, x1, gam, mean, rstd, dyb, dyf, add0, None, dg, db, seg)
+    edg, edb = torch.zeros(D), torch.zeros(D)
+    edx0, edx1 = E.layernorm_bwd(x0.cpu(), None if x1 is None else x1.cpu(), gam.cpu(), emean, erstd, dyb.cpu(), dyf.cpu(),
+                                 add0.cpu(), None, edg, edb, seg)
+    close(dx0, edx0, 1e-3, 1e-3, "dx0")
+    if n1:
+        close(dx1, edx1, 1e-3, 1e-3, "dx1")
+    close(dg, edg, 1e-3, 1e-2, "dgamma"); close(db, edb, 1e-3, 1e-2, "dbeta")
+
+
+# ---------------------------------------------------------------- GEMM
+GEMM_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests')
+import deepavfusion_b200.kernels as K
+import cpu_kernels as E
+bf16 = torch.bfloat16
+def rnd(*s, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*s, generator=g).to(dtype).cuda()
+impl = int(sys.argv[1])
+K.set_gemm_impl(impl)
+fails = 0
+def check(name, got, ref, rtol=2e-2, atol=2e-2):
+    global fails
+    got, ref = got.float().cpu(), ref.float().cpu()
+    rel = float((got - ref).norm() / (ref.norm() + 1e-30))
+    ok = rel < 1e-2 and bool(((got - ref).abs() <= atol + rtol * ref.abs()).all())
+    print(('OK   ' if ok else 'FAIL ') + name + f' rel-L2 {{rel:.2e}} max {{float((got-ref).abs().max()):.2e}}', flush=True)
+    fails += (not ok)
+shapes = [(128, 128, 64), (256, 256, 128), (3136, 768, 768), (1216, 2304, 768), (98, 192, 768), (512, 1536, 768), (14592, 512, 2048), (300, 72, 136)]
+for (M, N, Kd) in shapes:
+    a, b = rnd(M, Kd, seed=1, dtype=bf16), rnd(N, Kd, seed=2, dtype=bf16)
+    ref = a.float() @ b.float().t()
+    check(f'fwd KK {{M}}x{{N}}x{{Kd}} f32', K.gemm(a, b, out_dtype=torch.float32), ref / 1, 1e-2, 1e-1 * (Kd / 768) ** 0.5)
+    # dgrad: A K-major [M,N], B stored [N,Kd] MN-major -> out [M,Kd]
+    dy = rnd(M, N, seed=3, dtype=bf16)
+    check(f'dgrad K,MN {{M}}x{{Kd}}x{{N}}', K.gemm(dy, b, True, False, out_dtype=torch.float32), dy.float() @ b.float(), 1e-2, 1e-1 * (N / 768) ** 0.5)
+    # wgrad: both MN-major, accumulate with auto split-K
+    out = torch.ones(N, Kd, device='cuda')
+    K.gemm(dy, a, False, False, out=out, accumulate=True)
+    check(f'wgrad MN,MN {{N}}x{{Kd}}x{{M}}', out, 1 + dy.float().t() @ a.float(), 1e-2, 1e-1 * (M / 768) ** 0.5)
+# epilogues
+M, N, Kd = 392, 3072, 768
+a, b = rnd(M, Kd, seed=4, dtype=bf16), rnd(N, Kd, seed=5, dtype=bf16) * 0.05
+bias = rnd(N, seed=6)
+(g, h) = K.gemm(a, b, bias=bias, act=K.ACT_GELU, want_aux=True)
+(eg, eh) = E.gemm(a.cpu(), b.cpu(), bias=bias.cpu(), act=E.ACT_GELU, want_aux=True)
+check('gelu out', g, eg); check('gelu aux', h, eh)
+dy = rnd(M, Kd, seed=7, dtype=bf16)
+dh = K.gemm(dy, b, True, False, act=K.ACT_DGELU, aux_in=h)
+check('dgelu', dh, E.gemm(dy.cpu(), b.cpu(), True, False, act=E.ACT_DGELU, aux_in=h.cpu()))
+# residual + row window + res_idx + bf16 column-sliced weight
+B_, F_, D_ = 8, 32, 768
+tok = rnd(B_ * 8, D_, seed=8, dtype=bf16); w = rnd(D_, D_, seed=9, dtype=bf16) * 0.05; bb = rnd(D_, seed=10)
+res = rnd(B_ * F_, D_, seed=11)
+out = torch.zeros(B_ * F_, D_, device='cuda'); eout = torch.zeros(B_ * F_, D_)
+_, aux = K.gemm(tok, w, bias=bb, want_aux=True, res=res, out=out, window=(8, F_, 16))
+_, eaux = E.gemm(tok.cpu(), w.cpu(), bias=bb.cpu(), want_aux=True, res=res.cpu(), out=eout, window=(8, F_, 16))
+check('window out', out, eout); check('window aux', aux, eaux)
+idx = torch.randint(0, B_ * F_, (B_ * 8,)).cuda()
+o2 = K.gemm(tok, w, res=res, res_idx=idx, out_dtype=torch.float32)
+check('res_idx', o2, E.gemm(tok.cpu(), w.cpu(), res=res.cpu(), res_idx=idx.cpu(), out_dtype=torch.float32))
+wk = rnd(192, 2 * D_, seed=12, dtype=bf16) * 0.05
+check('col-slice B', K.gemm(tok, wk[:, D_:], out_dtype=torch.float32), tok.float() @ wk[:, D_:].float().t())
+gk = torch.zeros(192, 2 * D_, device='cuda')
+dyk = rnd(B_ * 8, 192, seed=13, dtype=bf16)
+K.gemm(dyk, tok, False, False, out=gk[:, D_:], accumulate=True)
+check('col-slice wgrad', gk[:, D_:], dyk.float().t() @ tok.float()); assert float(gk[:, :D_].abs().max()) == 0
+torch.cuda.synchronize()
+print('FAILS', fails)
+sys.exit(1 if fails else 0)
+"""
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_gemm_all_modes(impl):
+    """Runs in a subprocess: a wrong tensor-core descriptor traps (bounded mbarrier spin) and poisons
+    the CUDA context; the rest of the suite must survive that."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", GEMM_SCRIPT.format(root=root), str(impl)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-6000:]); print(r.stderr[-3000:])
+    assert r.returncode == 0, "GEMM mismatches:\n" + "\n".join(l for l in r.stdout.splitlines() if l.startswith("FAIL")) + r.stderr[-1500:]
+
+
+# ---------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,H,Nq,Nk,dqk,dv,skip", [(4, 12, 49, 81, 64, 64, 32), (3, 16, 228, 228, 32, 32, 0), (5, 12, 16, 8, 16, 64, 0),
+                                                   (2, 12, 8, 19, 64, 64, 0), (2, 2, 4, 1, 64, 64, 0), (2, 12, 196, 228, 64, 64, 32)])
+def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip):
+    scale = 0.125
+    if dqk == dv:       # packed qkv buffer with a dead query prefix, like the encoder blocks
+        S = Nk
+        qkv = rnd(B, S, 3, H, dqk, seed=20, dtype=bf16)
+        q, k, v = qkv[:, skip:skip + Nq, 0], qkv[:, :, 1], qkv[:, :, 2]
+    else:
+        q, k, v = rnd(B, Nq, H, dqk, seed=21, dtype=bf16), rnd(B, Nk, H, dqk, seed=22, dtype=bf16), rnd(B, Nk, H, dv, seed=23, dtype=bf16)
+    o, lse = K.attention_fwd(q, k, v, scale)
+    eo, else_ = E.attention_fwd(q.cpu(), k.cpu(), v.cpu(), scale)
+    close(o, eo, 2e-2, 2e-2, "attn o"); close(lse, else_, 1e-3, 1e-3, "lse")
+    do = rnd(B, Nq, H, dv, seed=24, dtype=bf16)
+    dq, dk, dvv = torch.zeros_like(q.contiguous()), torch.zeros_like(k.contiguous()), torch.zeros_like(v.contiguous())
+    K.attention_bwd(q, k, v, do, lse, scale, dq, dk, dvv)
+    edq, edk, edv = torch.zeros(q.shape, dtype=bf16), torch.zeros(k.shape, dtype=bf16), torch.zeros(v.shape, dtype=bf16)
+    E.attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), lse.cpu(), scale, edq, edk, edv)
+    close(dq, edq, 3e-2, 3e-2, "dq"); close(dk, edk, 3e-2, 3e-2, "dk"); close(dvv, edv, 3e-2, 3e-2, "dv")
+    K.attention_bwd(q, k, v, do, lse, scale, dq, dk, dvv, accumulate_dq=True)
+    close(dq, 2 * edq.float(), 4e-2, 4e-2, "dq accumulate")
+
+
+# ---------------------------------------------------------------- decoder assembly / loss / optimizer
+def test_decoder_assemble(K):
+    B, nK, nF, L, D = 4, 49, 32, 196, 512
+    e, ef, mt, pos = rnd(B * nK, D, seed=30), rnd(B * nF, D, seed=31), rnd(D, seed=32), rnd(L, D, seed=33)
+    noise = torch.rand(B, L, generator=torch.Generator().manual_seed(34))
+    ir, ik, _ = E.mask_rank(noise, nK)
+    seq = K.decoder_assemble_fwd(e, ef, mt, pos, ir.cuda(), nK, nF)
+    assert torch.equal(seq.cpu(), E.decoder_assemble_fwd(e.cpu(), ef.cpu(), mt.cpu(), pos.cpu(), ir, nK, nF))
+    dseq = rnd(B, nF + L, D, seed=35)
+    dm, dp = torch.zeros(D, device="cuda"), torch.zeros(L, D, device="cuda")
+    de, df = K.decoder_assemble_bwd(dseq, ik.cuda(), ir.cuda(), nF, dm, dp)
+    edm, edp = torch.zeros(D), torch.zeros(L, D)
+    ede, edf = E.decoder_assemble_bwd(dseq.cpu(), ik, ir, nF, edm, edp)
+    assert torch.equal(de.cpu(), ede) and torch.equal(df.cpu(), edf)
+    close(dm, edm, 1e-4, 1e-3, "dmask_token"); close(dp, edp, 1e-5, 1e-5, "dpos")
+
+
+@pytest.mark.parametrize("C,H,W,norm", [(3, 224, 224, True), (1, 128, 192, True), (3, 64, 64, False)])
+def test_masked_mse(K, C, H, W, norm):
+    B, p = 4, 16
+    L, P = (H // p) * (W // p), p * p * C
+    img, pred = rnd(B, C, H, W, seed=40), rnd(B * L, P, seed=41)
+    mask = (torch.rand(B, L, generator=torch.Generator().manual_seed(42)) > 0.25).float().cuda()
+    ls = K.masked_mse_fwd(img, pred, mask, p, L, 0, norm)
+    close(ls, E.masked_mse_fwd(img.cpu(), pred.cpu(), mask.cpu(), p, L, 0, norm), 1e-4, 1e-4, "loss sum")
+    gs = torch.tensor([0.7], device="cuda")
+    dp = K.masked_mse_bwd(img, pred, mask, gs, 1.0 / float(mask.sum()), p, L, 0, norm)
+    edp = E.masked_mse_bwd(img.cpu(), pred.cpu(), mask.cpu(), gs.cpu(), 1.0 / float(mask.sum()), p, L, 0, norm)
+    close(dp, edp, 1e-2, 1e-7, "dpred")
+
+
+def test_adamw_and_sumsq(K):
+    from oracle.avmae_oracle import adamw_step as oracle_adamw
+    n = 64 * 1000
+    p, g = rnd(n, seed=50), rnd(n, seed=51) * 0.01
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.zeros(n, dtype=bf16, device="cuda")
+    seg_end = [64 * 300, n]
+    hp = torch.tensor([1e-3, 0.0, 5e-4, 0.05], device="cuda")
+    P = [p.cpu()[:seg_end[0]].clone(), p.cpu()[seg_end[0]:].clone()]
+    G = [g.cpu()[:seg_end[0]].clone(), g.cpu()[seg_end[0]:].clone()]
+    Mo, Vo = [torch.zeros_like(x) for x in P], [torch.zeros_like(x) for x in P]
+    ss = torch.zeros(1, device="cuda")
+    K.sumsq_f32(g, ss)
+    close(ss, (g.double() ** 2).sum().float().reshape(1), 1e-5, 0, "sumsq")
+    b1, b2 = 0.9, 0.95
+    for step in (1, 2, 3):
+        scal = torch.tensor([b1 ** step, b2 ** step, 1.0, 0.0], device="cuda")
+        gk = g.clone()
+        K.adamw_step(p, gk, m, v, pb, seg_end, hp, scal, b1, b2, 1e-8, True)
+        assert float(gk.abs().max()) == 0
+        for s_, (lr, wd) in enumerate(((1e-3, 0.0), (5e-4, 0.05))):
+            oracle_adamw(P[s_], G[s_], Mo[s_], Vo[s_], step, lr, b1, b2, 1e-8, wd)
+    close(p, torch.cat(P), 1e-5, 1e-6, "adamw p"); close(m, torch.cat(Mo), 1e-5, 1e-8, "adamw m"); close(v, torch.cat(Vo), 1e-5, 1e-10, "adamw v")
+    assert torch.equal(pb.cpu(), p.cpu().to(bf16))

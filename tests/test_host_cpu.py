@@ -1,0 +1,143 @@
+"""CPU: host-side orchestration (autograd wiring, gradient routing into the flat buffers, state_dict
+contract, fail-loud behaviour) with the CUDA kernels replaced by their torch emulations, against the
+oracle.  No CUDA compute is involved; the kernels themselves are checked by the -m gpu tests."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import avmae_oracle as O
+import cpu_kernels
+import model_utils as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    cpu_kernels.install(monkeypatch)
+
+
+@pytest.mark.parametrize("kw,B", [({}, 3), (dict(fusion_attn_ratio=1.0, fusion_mlp_ratio=4.0), 2),
+                                  (dict(fusion_layers="1", depth=3), 2), (dict(fusion_layers="none"), 2)])
+def test_model_orchestration_vs_oracle(emulated, kw, B):
+    cfg = U.tiny_cfg(**kw)
+    sd = O.build_state(cfg, seed=0)
+    image, audio = U.make_inputs(cfg, B)
+    ni, na = U.make_noise(cfg, B)
+    out, grads = O.loss_and_grads(sd, cfg, image, audio, ni, na)
+    _, amp_grads = O.loss_and_grads(sd, cfg, image, audio, ni, na, amp=True)
+    model = U.build_model(cfg)
+    model.load_state_dict(sd, strict=True)
+    with U.inject_rand([ni, na]):
+        li, la, pi, pa = model(image, audio)
+    (li + la).backward()
+    assert abs(li.item() - out["loss_image"].item()) < 2e-3 * out["loss_image"].item()
+    assert abs(la.item() - out["loss_audio"].item()) < 2e-3 * out["loss_audio"].item()
+    named = dict(model.named_parameters())
+    if kw.get("fusion_layers") == "none":       # fusion tokens only feed the decoders then
+        grads = {k: v for k, v in grads.items() if v is not None}
+    failures, worst, glob = U.grad_report(named, grads, amp_grads)
+    assert not failures, failures[:5]
+    assert glob < 2e-2
+    # gradients live in the flat buffer, frozen pos-embeds have none
+    st = model._davf_store
+    for k, p in named.items():
+        if p.requires_grad:
+            assert p.grad.data_ptr() == st.grad(p).data_ptr()
+    assert named["encoder.image.pos_embed"].grad is None
+
+
+def test_gradient_accumulation_and_zero_grad(emulated):
+    cfg = U.tiny_cfg()
+    model = U.build_model(cfg)
+    image, audio = U.make_inputs(cfg, 2)
+    ni, na = U.make_noise(cfg, 2)
+    def step():
+        with U.inject_rand([ni, na]):
+            li, la, _, _ = model(image, audio)
+        (li + la).backward()
+    step()
+    g1 = model._davf_store.flat_g.clone()
+    step()
+    assert torch.allclose(model._davf_store.flat_g, 2 * g1, rtol=1e-4, atol=1e-7)      # += semantics (misc.py:144-148)
+    torch.optim.SGD(model.parameters(), lr=0.1).zero_grad()                             # set_to_none=True
+    assert all(p.grad is None for p in model.parameters())
+    step()
+    assert torch.allclose(model._davf_store.flat_g, g1, rtol=1e-4, atol=1e-7)
+    assert all(p.grad is not None for p in model.parameters() if p.requires_grad)
+
+
+def test_state_dict_roundtrip_and_shadow_refresh(emulated):
+    cfg = U.tiny_cfg()
+    model = U.build_model(cfg)
+    image, audio = U.make_inputs(cfg, 1)
+    ni, na = U.make_noise(cfg, 1)
+    with U.inject_rand([ni, na]):
+        l0 = model(image, audio)[0].item()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(1.5)
+    with U.inject_rand([ni, na]):
+        l1 = model(image, audio)[0].item()
+    assert abs(l1 - l0) > 1e-4                       # in-place edits reach the bf16 shadows
+    model.load_state_dict(sd, strict=True)
+    with U.inject_rand([ni, na]):
+        l2 = model(image, audio)[0].item()
+    assert abs(l2 - l0) < 1e-6
+
+
+def test_encoder_api_contract(emulated):
+    cfg = U.tiny_cfg()
+    model = U.build_model(cfg)
+    enc = model.encoder
+    image, audio = U.make_inputs(cfg, 2)
+    xi, xa, xf, embs = enc(image, audio, return_embs=True)
+    assert xi.shape == (2, 16, 128) and xa.shape == (2, 12, 128) and xf.shape == (2, 32, 128) and len(embs) == cfg.depth
+    sd = {k: v for k, v in model.state_dict().items()}
+    ref = O.encoder_forward(O._Prec(False), sd, cfg, image, audio)
+    for a, b in zip((xi, xa, xf), ref):
+        assert ((a - b).norm() / b.norm()).item() < 2e-2
+    assert enc.embed_dim == 128 and enc.image.patch_embed.grid_size == (4, 4) and enc.image.patch_embed.patch_size == (16, 16)
+    ids = enc.params_layer_ids()
+    assert max(l for _, l in ids) == cfg.depth + 1
+    # every trainable encoder parameter appears exactly once (lr_sched.py:32 builds a dict from it)
+    assert {id(p) for p, _ in ids if p is not None} == {id(p) for p in enc.parameters() if p.requires_grad}
+
+
+def test_unsupported_options_fail_loudly():
+    from deepavfusion_b200.models import DeepAVFusion
+    with pytest.raises(NotImplementedError):
+        DeepAVFusion(image_pretrained="", audio_pretrained="", drop_path=0.2)
+    with pytest.raises(NotImplementedError):
+        DeepAVFusion(image_pretrained="", audio_pretrained="", fusion_arch="dense_mmi")
+
+
+def test_cpu_model_without_kernels_fails_loudly():
+    cfg = U.tiny_cfg()
+    model = U.build_model(cfg)
+    image, audio = U.make_inputs(cfg, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(image, audio)
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly what include/davf.h declares (no compute calls)."""
+    from deepavfusion_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "davf.h")).read()
+    declared = set(re.findall(r"\b(davf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    if not os.path.exists(_cabi.LIB_PATH):
+        _cabi.build()
+    handle = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    lib = _cabi.lib()
+    assert lib.davf_version() == 1
+    # argument validation happens before any CUDA call
+    assert lib.davf_set_gemm_impl(7) == -1 and b"set_gemm_impl" in lib.davf_last_error()
+    assert lib.davf_mask_rank(None, 1, 4, 9, None, None, None, None) == -1

@@ -1,0 +1,91 @@
+"""CPU: the oracle against the fixtures written from the REAL reference (oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import avmae_oracle as O
+import model_utils as U
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _digest(t):
+    import hashlib
+    return hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+@pytest.mark.parametrize("name,cfg,B,nparams", [
+    ("vggsound_b2", O.OracleConfig(fusion_attn_ratio=0.25, fusion_mlp_ratio=1.0), 2, 320_563_712),
+    ("audioset_b1", O.OracleConfig(fusion_attn_ratio=1.0, fusion_mlp_ratio=4.0), 1, 378_997_760),
+])
+def test_oracle_matches_reference_fixture(name, cfg, B, nparams):
+    meta = json.load(open(os.path.join(GOLD, f"{name}.json")))
+    gold = np.load(os.path.join(GOLD, f"{name}.npz"))
+    shapes = O.state_shapes(cfg)
+    assert {k: list(v) for k, v in shapes.items()} == meta["state_shapes"]          # 893-key state_dict contract
+    assert sum(int(np.prod(s)) for s in shapes.values()) == nparams == meta["n_params"]   # checkpoint-size KAT
+    sd = O.build_state(cfg, seed=0)
+    image, audio = U.make_inputs(cfg, B)
+    # the recipe must regenerate the exact tensors the fixture was made from
+    assert _digest(image) == meta["digests"]["image"] and _digest(audio) == meta["digests"]["audio"]
+    assert _digest(torch.cat([sd[k].flatten()[:64] for k in sorted(sd)])) == meta["digests"]["state"]
+    ni, na = torch.from_numpy(gold["noise_image"]), torch.from_numpy(gold["noise_audio"])
+    out, grads = O.loss_and_grads(sd, cfg, image, audio, ni, na)
+    assert torch.equal(out["image_ids_keep"], torch.from_numpy(gold["image_ids_keep"]))
+    assert torch.equal(out["image_ids_restore"], torch.from_numpy(gold["image_ids_restore"]))
+    assert torch.equal(out["image_mask"], torch.from_numpy(gold["image_mask"]))
+    assert torch.equal(out["audio_ids_keep"], torch.from_numpy(gold["audio_ids_keep"]))
+    assert abs(out["loss_image"].item() - float(gold["loss_image"])) < 1e-5 * float(gold["loss_image"])
+    assert abs(out["loss_audio"].item() - float(gold["loss_audio"])) < 1e-5 * float(gold["loss_audio"])
+    np.testing.assert_allclose(out["pred_image"][:, :4, :16].numpy(), gold["pred_image_head"], rtol=1e-3, atol=1e-4)
+    keys = meta["grad_keys"]
+    assert set(keys) == set(grads)
+    norms = np.array([grads[k].double().norm().item() for k in keys])
+    big = gold["grad_norms"] > 1e-6
+    np.testing.assert_allclose(norms[big], gold["grad_norms"][big], rtol=2e-3)
+    heads = np.stack([np.pad(grads[k].flatten()[:8].numpy(), (0, max(0, 8 - grads[k].numel()))) for k in keys])
+    np.testing.assert_allclose(heads, gold["grad_heads"], rtol=5e-2, atol=1e-5 * float(gold["grad_norm_global"]))
+    # self-consistency identities
+    assert float(out["image_mask"].sum()) == B * (196 - 49) and float(out["audio_mask"].sum()) == B * (96 - 19)
+    for k in keys:                                     # zero K-bias gradients (softmax shift invariance)
+        if k.endswith("attn.k.bias"):
+            assert grads[k].norm().item() < 1e-4 * float(gold["grad_norm_global"])
+
+
+def test_mask_ties_fixture():
+    d = np.load(os.path.join(GOLD, "mask_ties.npz"))
+    k, m, r = O.random_masking(torch.from_numpy(d["noise"]), 0.75)
+    assert (k.numpy() == d["ids_keep"]).all() and (r.numpy() == d["ids_restore"]).all() and (m.numpy() == d["mask"]).all()
+    # inverse-permutation identity
+    assert torch.equal(torch.gather(r, 1, k), torch.arange(k.shape[1]).expand(k.shape[0], -1))
+
+
+def test_pair_factorisation_identity():
+    """softmax over the 8x8 (v,a) pairs == outer product of two 8-way softmaxes."""
+    torch.manual_seed(0)
+    D, qk, nv, na = 64, 16, 8, 8
+    v, a, q = torch.randn(nv, D).double(), torch.randn(na, D).double(), torch.randn(5, qk).double()
+    Wk, bk, Wv, bv = torch.randn(qk, 2 * D).double(), torch.randn(qk).double(), torch.randn(D, 2 * D).double(), torch.randn(D).double()
+    xva = torch.cat([v[:, None].expand(-1, na, -1), a[None].expand(nv, -1, -1)], -1).flatten(0, 1)
+    ref = torch.softmax(q @ (xva @ Wk.t() + bk).t() * 0.125, -1) @ (xva @ Wv.t() + bv)
+    pv = torch.softmax(q @ (v @ Wk[:, :D].t() + bk).t() * 0.125, -1)
+    pa = torch.softmax(q @ (a @ Wk[:, D:].t()).t() * 0.125, -1)
+    fac = pv @ (v @ Wv[:, :D].t() + bv) + pa @ (a @ Wv[:, D:].t())
+    assert (ref - fac).abs().max().item() < 1e-12
+
+
+def test_adamw_restatement_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(1000)
+    g = torch.randn(1000) * 0.1
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    m, v, mine = torch.zeros(1000), torch.zeros(1000), p.clone()
+    for step in (1, 2, 3):
+        ref.grad = g.clone()
+        opt.step()
+        O.adamw_step(mine, g, m, v, step, 1e-3, 0.9, 0.95, 1e-8, 0.05)
+    assert (mine - ref.detach()).abs().max().item() < 1e-6
