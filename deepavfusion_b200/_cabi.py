@@ -98,7 +98,7 @@ SIGNATURES = {
     "davf_decoder_assemble_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
     "davf_masked_mse_fwd": (i, [vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
     "davf_masked_mse_bwd": (i, [vp, vp, vp, vp, f, vp, i, i, i, i, i, i, i, i, vp]),
-    "davf_adamw_step": (i, [vp, vp, vp, vp, vp, i64, vp, vp, i, vp, f, f, f, i, vp]),
+    "davf_adamw_step": (i, [vp, vp, vp, vp, vp, i64, vp, vp, vp, f, f, f, i, vp, vp]),
     "davf_sumsq_f32": (i, [vp, i64, vp, vp]),
     "davf_cast_flat_bf16": (i, [vp, vp, i64, vp]),
 }

@@ -1,48 +1,59 @@
 // K13/K14: fused multi-tensor AdamW over flat f32 buffers (replaces torch.optim.AdamW at
-// train.py:93 / misc.py:126-130, the /accum_iter sweep misc.py:114-119, zero_grad and the bf16
-// weight casts of autocast) and the global gradient sum-of-squares (misc.py:151-163).
-// Bandwidth-bound: 28 B/param algorithmic (read p,g,m,v; write p,m,v) + 2 B bf16 copy + 4 B zeroed g.
+// train.py:93 / misc.py:126-130, the /accum_iter sweep misc.py:114-119, zero_grad, the global
+// gradient norm misc.py:151-163 and the bf16 weight casts of autocast) in ONE pass.
+// Bandwidth-bound: 28 B/param algorithmic (read p,g,m,v; write p,m,v) + 2 B bf16 shadow + 4 B zeroed g.
+// Per-parameter-group hyper-parameters come from device tables (a group id per 64-element chunk
+// and {lr, weight_decay} per group) so LR schedules never re-capture a CUDA graph and arbitrary
+// groupings (weight-decay split, "pretrained" groups, layer-wise lr decay) cost nothing.
 #include "common.cuh"
 
 namespace davf {
 
-constexpr int kMaxSeg = 16;
-struct SegTable { int64_t end4[kMaxSeg]; int nseg; };   // exclusive ends in float4 units
+constexpr int kChunk = 64;          // elements per group-table entry (== ParamStore.ALIGN)
+constexpr int kFrozen = 255;
 
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
-                                                    float4* __restrict__ v, uint2* __restrict__ pb, int64_t n4, SegTable seg,
-                                                    const float* __restrict__ hp, const float* __restrict__ scal, float beta1,
-                                                    float beta2, float eps, int zero_grad) {
+                                                    float4* __restrict__ v, uint2* __restrict__ pb, int64_t n4,
+                                                    const uint8_t* __restrict__ chunk_group, const float* __restrict__ hp,
+                                                    const float* __restrict__ scal, float beta1, float beta2, float eps,
+                                                    int zero_grad, float* __restrict__ sumsq_out) {
+  __shared__ float scratch[32];
   const float bc1 = 1.0f - scal[0], bc2 = 1.0f - scal[1], gsc = scal[2];
   const float inv_sqrt_bc2 = rsqrtf(bc2);
+  float ss = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    int k = 0;
-#pragma unroll
-    for (int j = 0; j < kMaxSeg - 1; ++j)
-      if (j < seg.nseg - 1 && i >= seg.end4[j]) k = j + 1;
-    const float lr = hp[2 * k], wd = hp[2 * k + 1];
-    const float step = lr / bc1, decay = 1.0f - lr * wd;
-    float4 P = p[i], G = g[i], M = m[i], V = v[i];
-    float* pp = reinterpret_cast<float*>(&P);
+    const int gid = chunk_group[i / (kChunk / 4)];
+    float4 G = g[i];
     float* gg = reinterpret_cast<float*>(&G);
-    float* mm = reinterpret_cast<float*>(&M);
-    float* vv = reinterpret_cast<float*>(&V);
+    if (gid != kFrozen) {
+      const float lr = hp[2 * gid], wd = hp[2 * gid + 1];
+      const float step = lr / bc1, decay = 1.0f - lr * wd;
+      float4 P = p[i], M = m[i], V = v[i];
+      float* pp = reinterpret_cast<float*>(&P);
+      float* mm = reinterpret_cast<float*>(&M);
+      float* vv = reinterpret_cast<float*>(&V);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float gr = gg[c] * gsc;
-      mm[c] = beta1 * mm[c] + (1.0f - beta1) * gr;
-      vv[c] = beta2 * vv[c] + (1.0f - beta2) * gr * gr;
-      const float denom = sqrtf(vv[c]) * inv_sqrt_bc2 + eps;
-      pp[c] = pp[c] * decay - step * (mm[c] / denom);
+      for (int c = 0; c < 4; ++c) {
+        const float gr = gg[c] * gsc;
+        ss = fmaf(gr, gr, ss);
+        mm[c] = beta1 * mm[c] + (1.0f - beta1) * gr;
+        vv[c] = beta2 * vv[c] + (1.0f - beta2) * gr * gr;
+        const float denom = sqrtf(vv[c]) * inv_sqrt_bc2 + eps;
+        pp[c] = pp[c] * decay - step * (mm[c] / denom);
+      }
+      p[i] = P; m[i] = M; v[i] = V;
+      if (pb) {
+        uint2 o;
+        o.x = pack_bf16x2(P.x, P.y);
+        o.y = pack_bf16x2(P.z, P.w);
+        pb[i] = o;
+      }
     }
-    p[i] = P; m[i] = M; v[i] = V;
     if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pb) {
-      uint2 o;
-      o.x = pack_bf16x2(P.x, P.y);
-      o.y = pack_bf16x2(P.z, P.w);
-      pb[i] = o;
-    }
+  }
+  if (sumsq_out) {
+    ss = block_sum(ss, scratch);
+    if (threadIdx.x == 0) atomicAdd(sumsq_out, ss);
   }
 }
 
@@ -61,26 +72,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g
 
 using namespace davf;
 
-extern "C" int davf_adamw_step(float* p, float* g, float* m, float* v, davf_bf16* p_bf16, int64_t n, const int64_t* seg_end,
-                               const float* hp, int nseg, const float* scal, float beta1, float beta2, float eps, int zero_grad,
-                               davf_stream_t s) {
-  DAVF_CHECK_ARG(p && g && m && v && hp && scal && seg_end, "adamw_step: null pointer");
-  DAVF_CHECK_ARG(n % 4 == 0 && nseg >= 1 && nseg <= kMaxSeg, "adamw_step: n=%lld nseg=%d", (long long)n, nseg);
-  SegTable seg;
-  seg.nseg = nseg;
-  int64_t prev = 0;
-  for (int i = 0; i < kMaxSeg; ++i) seg.end4[i] = n / 4;
-  for (int i = 0; i < nseg; ++i) {
-    DAVF_CHECK_ARG(seg_end[i] % 4 == 0 && seg_end[i] >= prev && seg_end[i] <= n, "adamw_step: segment %d end %lld", i, (long long)seg_end[i]);
-    seg.end4[i] = seg_end[i] / 4;
-    prev = seg_end[i];
-  }
+extern "C" int davf_adamw_step(float* p, float* g, float* m, float* v, davf_bf16* p_bf16, int64_t n,
+                               const uint8_t* chunk_group, const float* hp, const float* scal, float beta1, float beta2,
+                               float eps, int zero_grad, float* sumsq_out, davf_stream_t s) {
+  DAVF_CHECK_ARG(p && g && m && v && hp && scal && chunk_group, "adamw_step: null pointer");
+  DAVF_CHECK_ARG(n % kChunk == 0, "adamw_step: n=%lld must be a multiple of %d", (long long)n, kChunk);
   if (n == 0) return DAVF_OK;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
   adamw_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
-                                                     reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p_bf16), n / 4, seg, hp, scal,
-                                                     beta1, beta2, eps, zero_grad);
+                                                     reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p_bf16), n / 4, chunk_group, hp,
+                                                     scal, beta1, beta2, eps, zero_grad, sumsq_out);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

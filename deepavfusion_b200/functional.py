@@ -54,6 +54,24 @@ def _f32_rows(t: Tensor) -> Tensor:
     return t.reshape(-1, t.shape[-1])
 
 
+def params_of(ns: SimpleNamespace):
+    """All nn.Parameters referenced by a region namespace (nested namespaces included)."""
+    out = []
+    for v in vars(ns).values():
+        if isinstance(v, nn.Parameter):
+            out.append(v)
+        elif isinstance(v, SimpleNamespace):
+            out.extend(params_of(v))
+    return out
+
+
+def _done(m: SimpleNamespace) -> None:
+    pl = m.__dict__.get("_plist")
+    if pl is None:
+        pl = m.__dict__["_plist"] = params_of(m)
+    m.store.done(pl)
+
+
 # --------------------------------------------------------------------------------------------
 # a2  patch embed (+pos, kept rows only)        vits.py:91-100, timm PatchEmbed
 # --------------------------------------------------------------------------------------------
@@ -82,6 +100,7 @@ class PatchEmbedFn(torch.autograd.Function):
         (a,) = ctx.saved_tensors
         dxb = K.cast_rows_bf16(_f32_rows(dx.contiguous()))
         linear_bwd(m.store, dxb, a, m.weight, m.bias, need_dx=False)
+        _done(m)
         return None, None, None, None
 
 
@@ -143,6 +162,7 @@ class AttnBranchFn(torch.autograd.Function):
         else:
             dx, _ = K.layernorm_bwd(x0, None, m.norm_w.data, mean, rstd, dxn, None, dy, None, gw, gb)
             dxp = None
+        _done(m)
         return dxp, dx, None, None
 
 
@@ -175,6 +195,7 @@ class MlpBranchFn(torch.autograd.Function):
         dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b)
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, dxn, None, dy.view(1, -1, D), None,
                                 st.grad(m.norm_w), st.grad(m.norm_b))
+        _done(m)
         return dx.view(dy.shape), None, None
 
 
@@ -200,6 +221,7 @@ class LayerNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, None, dy.view(-1, dy.shape[-1]), None, None,
                                 st.grad(m.norm_w), st.grad(m.norm_b))
+        _done(m)
         return dx.view(dy.shape), None, None
 
 
@@ -323,6 +345,7 @@ class FusionAttnFn(torch.autograd.Function):
         seg = [0, nmm, nmm + nv, F]
         dxmm, _ = K.layernorm_bwd(xmm, None, m.n_mm_w.data, mean_m, rstd_m, dseg, d2, None, None,
                                   st.grad(m.n_mm_w), st.grad(m.n_mm_b), seg_start=seg)
+        _done(m)
         return dxmm, dxv, dxa, None, None
 
 
@@ -359,6 +382,7 @@ class DecoderEmbedFn(torch.autograd.Function):
                                         st.grad(m.mask_token).view(Dd), st.grad(m.pos_embed).view(L, Dd))
         dx = linear_bwd(st, de, xb, m.embed_w, m.embed_b, out_dtype=torch.float32)
         dxf = linear_bwd(st, df, xfb, m.embed_w, m.embed_b, out_dtype=torch.float32)
+        _done(m)
         return dx.view(B, nK, D), dxf.view(B, nF, D), None, None, None, None
 
 
@@ -401,4 +425,5 @@ class PredLossFn(torch.autograd.Function):
         dseq[:, :nF].zero_()
         K.layernorm_bwd(seq[:, nF:], None, m.norm_w.data, mean, rstd, dxn, None, None, None,
                         st.grad(m.norm_w), st.grad(m.norm_b), dx0_out=dseq[:, nF:])
+        _done(m)
         return dseq, None, None, None, None

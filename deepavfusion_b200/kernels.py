@@ -345,13 +345,17 @@ def masked_mse_bwd(img: Tensor, pred: Tensor, mask: Tensor, gscale: Tensor, inv_
 # --------------------------------------------------------------------------------------------
 # optimizer
 # --------------------------------------------------------------------------------------------
-def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p_bf16: Optional[Tensor], seg_end: Sequence[int],
-               hp: Tensor, scal: Tensor, beta1: float, beta2: float, eps: float, zero_grad: bool) -> None:
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, p_bf16: Optional[Tensor], chunk_group: Tensor,
+               hp: Tensor, scal: Tensor, beta1: float, beta2: float, eps: float, zero_grad: bool,
+               sumsq_out: Optional[Tensor] = None) -> None:
+    """Fused AdamW over the flat buffers; chunk_group u8 [n/64] (255 = frozen), hp f32 [ngroups*2],
+    scal f32 [4] = {beta1^t, beta2^t, grad_scale, -}; all tables on the device."""
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (hp, "hp"), (scal, "scal")):
         _need(t, torch.float32, n)
-    arr = (C.c_int64 * len(seg_end))(*[int(x) for x in seg_end])
-    check(_cabi.lib().davf_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), C.cast(arr, C.c_void_p),
-                                     _ptr(hp), len(seg_end), _ptr(scal), beta1, beta2, eps, int(zero_grad), _stream()),
+    _need(chunk_group, torch.uint8, "chunk_group")
+    assert chunk_group.numel() * 64 == p.numel()
+    check(_cabi.lib().davf_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), _ptr(chunk_group),
+                                     _ptr(hp), _ptr(scal), beta1, beta2, eps, int(zero_grad), _ptr(sumsq_out), _stream()),
           "davf_adamw_step")
 
 

@@ -9,9 +9,8 @@ autocast re-casts on every forward in the reference).
 
 Parameters stay ordinary ``nn.Parameter`` objects: ``state_dict()``, ``named_parameters()``,
 ``load_state_dict(strict=True)``, ``torch.optim`` and ``param.grad`` consumers (misc.py:151-163)
-keep working.  Order inside the buffers is by optimizer group class so that every param group of
-util/lr_sched.py:77-92 is a union of contiguous segments:
-    (other | encoder.image | encoder.audio) x (no_decay | decay).
+keep working.  Order inside the buffers is the order of first use in the forward pass, so that
+gradient buckets (contiguous ranges) complete in reverse order during backward.
 """
 from __future__ import annotations
 
@@ -23,13 +22,41 @@ from torch import nn
 ALIGN = 64          # elements; keeps every tensor 256-byte (f32) / 128-byte (bf16) aligned for TMA
 
 
-def group_class(name: str, p: torch.Tensor) -> int:
-    """0..5 = region*2 + decay.  no_decay rule = timm param_groups_weight_decay (ndim <= 1 or
-    '.bias') plus train.py:88 ('bias' or 'norm' in the name)."""
-    region = 1 if name.startswith("encoder.image.") or name.startswith("image.") else \
-        2 if name.startswith("encoder.audio.") or name.startswith("audio.") else 0
-    no_decay = p.ndim <= 1 or name.endswith(".bias") or "bias" in name or "norm" in name
-    return region * 2 + (0 if no_decay else 1)
+import re
+
+_BLK = re.compile(r"^(?:encoder\.)?(image|audio)\.blocks\.(\d+)\.")
+_FUS = re.compile(r"^(?:encoder\.)?fusion_blocks\.(\d+)\.")
+_DEC = re.compile(r"^(image|audio)_decoder_(\w+?)(?:\.(\d+))?(?:\.|$)")
+
+
+def forward_order_key(name: str):
+    """Sort key = position of the parameter's FIRST use in the forward pass (deepavfusion.py:88-113,
+    avmae.py:216-236).  Backward produces gradients in the reverse order, so gradient buckets cut
+    from the END of the flat buffer complete early and their all-reduce overlaps the rest of
+    backward (what DDP's bucket order does in the reference, misc.py:34)."""
+    base = name[len("encoder."):] if name.startswith("encoder.") else name
+    if base == "fusion_tokens":
+        return (0, 0, 0)
+    m = _BLK.match(name)
+    if m:
+        return (2, int(m.group(2)), 0 if m.group(1) == "image" else 1)
+    m = _FUS.match(name)
+    if m:
+        return (2, int(m.group(1)), 2)
+    if base.startswith(("image.patch_embed", "image.pos_embed", "image.cls_token")):
+        return (1, 0, 0)
+    if base.startswith(("audio.patch_embed", "audio.pos_embed", "audio.cls_token")):
+        return (1, 1, 0)
+    if base.startswith(("image.norm", "audio.norm", "fusion_norm")):
+        return (3, 0, 0)
+    m = _DEC.match(name)
+    if m:
+        stage = 4 if m.group(1) == "image" else 5
+        what = m.group(2)
+        if what == "blocks":
+            return (stage, 1 + int(m.group(3)), 0)
+        return (stage, 0 if what in ("embed", "mask_token", "pos_embed") else 100, 0)
+    return (9, 0, 0)
 
 
 class ParamStore:
@@ -37,16 +64,15 @@ class ParamStore:
         named = [(n, p) for n, p in module.named_parameters()]
         assert named, "module has no parameters"
         dev = named[0][1].device
-        order = sorted(range(len(named)), key=lambda i: (group_class(*named[i]), i))
+        order = sorted(range(len(named)), key=lambda i: (forward_order_key(named[i][0]), i))
         self.names: List[str] = []
         self.params: List[nn.Parameter] = []
         self.offsets: List[int] = []
-        self.classes: List[int] = []
         off = 0
         for i in order:
             n, p = named[i]
             assert p.dtype == torch.float32, f"{n}: master parameters must be f32"
-            self.names.append(n); self.params.append(p); self.offsets.append(off); self.classes.append(group_class(n, p))
+            self.names.append(n); self.params.append(p); self.offsets.append(off)
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
         self.device = dev
@@ -68,6 +94,7 @@ class ParamStore:
                     p.grad = self._g[k]
         self._versions = None
         self._depth = 0
+        self.sync = None          # optional util.distributed.GradSync (data-parallel bucket all-reduce)
         self.refresh_lowp(force=True)
 
     # -- re-entrancy: nested module forwards skip the per-forward checks ------------------------
@@ -151,14 +178,16 @@ class ParamStore:
             if p.requires_grad and not self._attached(p, k):
                 p.grad = self._g[k]
 
-    # -- optimizer segments ----------------------------------------------------------------------
-    def segments(self) -> List[Tuple[int, int, int]]:
-        """[(class, begin, end)] contiguous element ranges per group class."""
-        segs: List[Tuple[int, int, int]] = []
-        for k, c in enumerate(self.classes):
-            end = self.offsets[k + 1] if k + 1 < len(self.offsets) else self.numel
-            if segs and segs[-1][0] == c:
-                segs[-1] = (c, segs[-1][1], end)
-            else:
-                segs.append((c, self.offsets[k], end))
-        return segs
+    def index_of(self, p: nn.Parameter) -> int:
+        return self._index[id(p)]
+
+    def span(self, k: int) -> Tuple[int, int]:
+        """[begin, end) element range of parameter k in the flat buffers (end includes alignment padding)."""
+        end = self.offsets[k + 1] if k + 1 < len(self.offsets) else self.numel
+        return self.offsets[k], end
+
+    def done(self, params) -> None:
+        """Called at the end of a backward region: the kernels producing these parameters' gradients
+        are all enqueued.  Drives the overlapped bucket all-reduce when data-parallel."""
+        if self.sync is not None:
+            self.sync.params_done([self._index[id(p)] for p in params if p.requires_grad])

@@ -1,0 +1,134 @@
+"""Data-parallel plumbing (mirror of the hot-path parts of reference util/distributed.py:66-100 and
+the DDP wrap at util/misc.py:32-34): one process per GPU, ``torch.distributed`` over NCCL / NVLink,
+and a bucketed gradient all-reduce that overlaps backward.
+
+The path shards over the batch; the only exchange step is the sum-all-reduce of the
+flat f32 gradient buffer once per optimizer step.  Buckets are contiguous ranges of that buffer cut
+from its END (parameters are laid out in forward order, so backward finishes them first); a bucket is
+launched on a side stream as soon as the last backward region touching it has enqueued its kernels.
+Division by world size is folded into the fused AdamW's grad_scale.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..params import ParamStore
+
+
+def is_dist_avail_and_initialized() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_world_size() -> int:
+    return dist.get_world_size() if is_dist_avail_and_initialized() else 1
+
+
+def get_rank() -> int:
+    return dist.get_rank() if is_dist_avail_and_initialized() else 0
+
+
+def init_from_env(backend: Optional[str] = None) -> int:
+    """torchrun-style init (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  The reference launcher's
+    NCCL_P2P_DISABLE=1 / NCCL_P2P_LEVEL=LOC (launcher.py:74-76) must NOT be inherited on an NVSwitch box."""
+    for bad in ("NCCL_P2P_DISABLE", "NCCL_P2P_LEVEL"):
+        os.environ.pop(bad, None)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, **kw)
+    return local
+
+
+class GradSync:
+    """Bucketed, backward-overlapped sum-all-reduce of ``store.flat_g`` (replaces DDP's reducer)."""
+
+    def __init__(self, store: ParamStore, bucket_mb: float = 64.0, group=None):
+        self.store = store
+        self.group = group
+        self.world = dist.get_world_size(group) if is_dist_avail_and_initialized() else 1
+        self.enabled = True                       # False while accumulating (DDP no_sync, misc.py:144-148)
+        target = int(bucket_mb * 1024 * 1024 / 4)
+        n = len(store.params)
+        # buckets of parameter indices, cut from the end of the buffer
+        self.buckets: List[List[int]] = []
+        cur: List[int] = []
+        size = 0
+        for k in range(n - 1, -1, -1):
+            b, e = store.span(k)
+            cur.append(k)
+            size += e - b
+            if size >= target:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {}
+        self.ranges = []
+        for bi, ks in enumerate(self.buckets):
+            lo = min(store.span(k)[0] for k in ks)
+            hi = max(store.span(k)[1] for k in ks)
+            self.ranges.append((lo, hi))
+            for k in ks:
+                self.bucket_of[k] = bi
+        self.trainable = [sum(1 for k in ks if store.params[k].requires_grad) for ks in self.buckets]
+        self.cuda = store.flat_g.is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self.reset()
+        store.sync = self
+
+    def reset(self):
+        self.pending = list(self.trainable)
+        self.seen = set()
+        self.launched = [False] * len(self.buckets)
+        self.handles = []
+
+    def params_done(self, idxs):
+        if not self.enabled or self.world <= 1:
+            return
+        for k in idxs:
+            if k in self.seen:
+                continue
+            self.seen.add(k)
+            bi = self.bucket_of[k]
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                self._launch(bi)
+
+    def _launch(self, bi: int):
+        if self.launched[bi]:
+            return
+        self.launched[bi] = True
+        lo, hi = self.ranges[bi]
+        buf = self.store.flat_g[lo:hi]
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.handles.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """End of backward: launch whatever is left (gradients that arrive through autograd itself, e.g.
+        ``fusion_tokens``), then make the compute stream wait for the communication stream."""
+        if not self.enabled or self.world <= 1:
+            return
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for h in self.handles:
+            h.wait()
+        self.reset()

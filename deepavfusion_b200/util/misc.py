@@ -1,0 +1,111 @@
+"""Training-step runtime (mirror of reference util/misc.py:27-163 ``Trainer``).
+
+Same constructor and methods (``autocast``, ``autosync``, ``step``, ``backward``, ``zero_grad``,
+``get_scale``, ``module_dict``) so ``train.py:97-103,163-170`` runs unchanged.  What differs is what
+they call: backward is the hand-written CUDA path, the DDP reducer is ``GradSync`` (bucketed NCCL
+all-reduce overlapped with backward), and unscale + /accum + grad-norm + AdamW + zero_grad + bf16
+weight refresh are ONE fused kernel.  The two per-step host syncs of the reference
+(train.py:166, misc.py:78-79) are gone: ``step`` returns the gradient norm as a 0-dim DEVICE tensor
+(``MetricLogger.update`` calls ``.item()`` on tensors, meters.py:101-102).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+
+from ..models.layers import ensure_store
+from . import distributed as dist_utils
+from .optim import FusedAdamW
+
+
+class Trainer:
+    def __init__(self, model, criterion=None, optimizer=None, accum_iter=1, use_amp=True, distributed=False,
+                 bucket_mb: float = 64.0):
+        """``optimizer``: a ``FusedAdamW``, or a ``torch.optim.AdamW`` built the reference way
+        (train.py:89-93) whose param groups / hyper-parameters are adopted by a FusedAdamW.
+        ``use_amp`` is accepted for signature compatibility: the tensor-core path always computes in bf16
+        with f32 accumulation (BASELINE.json), which needs no GradScaler."""
+        self.distributed = bool(distributed) and dist_utils.get_world_size() > 1
+        self.model_without_ddp = model
+        self.model = model
+        self.n_steps = torch.tensor([0])
+        self.criterion = criterion
+        self.store = ensure_store(model)
+        if optimizer is not None and not isinstance(optimizer, FusedAdamW):
+            if not isinstance(optimizer, torch.optim.AdamW):
+                raise TypeError("Trainer drives the fused AdamW kernel; pass a torch.optim.AdamW (train.py:93) or a FusedAdamW")
+            groups = [{k: v for k, v in g.items() if k in ("params", "lr", "betas", "eps", "weight_decay", "lr_scale", "pretrained")}
+                      for g in optimizer.param_groups]
+            d = optimizer.defaults
+            optimizer = FusedAdamW(groups, self.store, lr=d["lr"], betas=d["betas"], eps=d["eps"], weight_decay=d["weight_decay"])
+        self.optimizer = optimizer
+        self.scaler = None
+        self.accum_iter = accum_iter
+        self.accums = 0
+        self.sync = dist_utils.GradSync(self.store, bucket_mb=bucket_mb) if self.distributed else None
+        if self.distributed:
+            self.broadcast_parameters()
+        world = dist_utils.get_world_size() if self.distributed else 1
+        if self.optimizer is not None:
+            self.optimizer.set_grad_scale(1.0 / (self.accum_iter * world))
+        self.eval_model = self.model_without_ddp
+        self.zero_grad()
+
+    def broadcast_parameters(self):
+        """Rank 0 -> all, once (what the DDP constructor does, misc.py:34): one flat buffer."""
+        torch.distributed.broadcast(self.store.flat_p, src=0)
+        self.store.refresh_lowp(force=True)
+
+    def module_dict(self):
+        d = {"state_dict": self.model_without_ddp, "n_steps": self.n_steps}
+        if self.criterion is not None:
+            d["criterion"] = self.criterion
+        if self.optimizer is not None:
+            d["optimizer"] = self.optimizer
+        return d
+
+    def zero_grad(self):
+        self.store.zero_grad()
+        self.accums = 0
+
+    def get_scale(self):
+        return 1.0
+
+    def backward(self, loss, create_graph=False):
+        assert not create_graph
+        if self.sync is not None:
+            self.sync.enabled = self.accums == self.accum_iter - 1       # all-reduce on the last micro-step only
+        loss.backward()
+        if self.sync is not None:
+            self.sync.finish()
+        self.accums += 1
+
+    def step(self, loss, create_graph=False, clip_grad=None, skip_grad=None):
+        if clip_grad is not None or skip_grad is not None:
+            raise NotImplementedError("clip_grad / skip_grad are unset in every pre-training config (deepavfusion.yaml:60)")
+        self.backward(loss, create_graph=create_graph)
+        norm = None
+        if self.accums == self.accum_iter:
+            self.optimizer.step(zero_grad=True)        # /accum/world, grad-norm^2, AdamW, bf16 refresh, zero_grad
+            norm = self.optimizer.grad_norm()
+            self.accums = 0
+            self.n_steps += 1
+        return norm, 1.0
+
+    def autocast(self):
+        return contextlib.nullcontext()
+
+    def autosync(self):
+        return contextlib.nullcontext()
+
+
+def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
+    """misc.py:151-163 for callers that still want it (one kernel over the flat buffer when possible)."""
+    parameters = [p for p in ([parameters] if isinstance(parameters, torch.Tensor) else parameters) if p.grad is not None]
+    if not parameters:
+        return torch.tensor(0.0)
+    if norm_type == math.inf:
+        return max(p.grad.detach().abs().max() for p in parameters)
+    return torch.norm(torch.stack([torch.norm(p.grad.detach(), norm_type) for p in parameters]), norm_type)

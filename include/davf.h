@@ -211,17 +211,19 @@ int davf_masked_mse_bwd(const float* img, const float* pred, const float* mask, 
                         int B, int C, int H, int W, int p, int pred_G, int pred_off, int norm_pix,
                         davf_stream_t s);
 
-/* ---- K13/K14: fused AdamW + grad-norm + bf16 weight refresh -----------------------------------
+/* ---- K13/K14: fused AdamW + grad-norm + zero_grad + bf16 weight refresh ---------------------------
  * Replaces torch.optim.AdamW (train.py:93; misc.py:126-130), the /accum_iter sweep (misc.py:114-119),
  * get_grad_norm_ (misc.py:151-163), zero_grad, and the per-step bf16 weight casts of autocast.
- * Works on flat f32 buffers p, g, m, v of n elements; group hyper-parameters come from a small
- * device table so that LR schedules do not re-capture CUDA graphs:
- *   seg_end i64 [nseg] (exclusive end offsets, ascending), hp f32 [nseg*2] = {lr, weight_decay},
+ * Works on flat f32 buffers p, g, m, v of n elements (n % 64 == 0).  Hyper-parameters live in DEVICE
+ * tables so LR schedules do not re-capture CUDA graphs and any parameter grouping is free:
+ *   chunk_group u8 [n/64]  group id of each 64-element chunk (255 = frozen: no update),
+ *   hp f32 [ngroups*2] = {lr, weight_decay} per group,
  *   scal f32 [4] = {beta1^t, beta2^t, grad_scale (1/accum or 1/(accum*world)), unused}.
- * p_bf16 (may be NULL) receives bf16(p_new); g is zeroed when zero_grad != 0. */
+ * p_bf16 (may be NULL) receives bf16(p_new); g is zeroed when zero_grad != 0; sumsq_out (may be
+ * NULL) += sum((g*grad_scale)^2) over the trainable chunks (the global grad-norm^2, no host sync). */
 int davf_adamw_step(float* p, float* g, float* m, float* v, davf_bf16* p_bf16, int64_t n,
-                    const int64_t* seg_end, const float* hp, int nseg, const float* scal,
-                    float beta1, float beta2, float eps, int zero_grad, davf_stream_t s);
+                    const uint8_t* chunk_group, const float* hp, const float* scal,
+                    float beta1, float beta2, float eps, int zero_grad, float* sumsq_out, davf_stream_t s);
 /* out[0] += sum(g^2) over n elements (global grad-norm; one pass, no host sync). */
 int davf_sumsq_f32(const float* g, int64_t n, float* out, davf_stream_t s);
 /* Plain f32 -> bf16 cast of a flat buffer (weight refresh after load_state_dict). */

@@ -244,22 +244,24 @@ def masked_mse_bwd(img, pred, mask, gscale, inv_count, p, pred_G, pred_off, norm
     return d.reshape(B * L, P).to(bf16)
 
 
-def adamw_step(p, g, m, v, p_bf16, seg_end, hp, scal, beta1, beta2, eps, zero_grad):
+def adamw_step(p, g, m, v, p_bf16, chunk_group, hp, scal, beta1, beta2, eps, zero_grad, sumsq_out=None):
     bc1, bc2, gsc = 1 - float(scal[0]), 1 - float(scal[1]), float(scal[2])
-    start = 0
-    for k, end in enumerate(seg_end):
-        lr, wd = float(hp[2 * k]), float(hp[2 * k + 1])
-        sl = slice(start, end)
-        gr = g[sl] * gsc
-        m[sl] = beta1 * m[sl] + (1 - beta1) * gr
-        v[sl] = beta2 * v[sl] + (1 - beta2) * gr * gr
-        denom = v[sl].sqrt() / math.sqrt(bc2) + eps
-        p[sl] = p[sl] * (1 - lr * wd) - (lr / bc1) * (m[sl] / denom)
-        start = end
+    gid = chunk_group.long().repeat_interleave(64)
+    live = gid != 255
+    gsafe = gid.clamp(max=hp.numel() // 2 - 1)
+    lr, wd = hp[2 * gsafe], hp[2 * gsafe + 1]
+    gr = g * gsc
+    if sumsq_out is not None:
+        sumsq_out += (gr[live].double() ** 2).sum().float()
+    m_new = beta1 * m + (1 - beta1) * gr
+    v_new = beta2 * v + (1 - beta2) * gr * gr
+    denom = v_new.sqrt() / math.sqrt(bc2) + eps
+    p_new = p * (1 - lr * wd) - (lr / bc1) * (m_new / denom)
+    m.copy_(torch.where(live, m_new, m)); v.copy_(torch.where(live, v_new, v)); p.copy_(torch.where(live, p_new, p))
     if zero_grad:
         g.zero_()
     if p_bf16 is not None:
-        p_bf16.copy_(p.to(bf16))
+        p_bf16.copy_(torch.where(live, p.to(bf16), p_bf16))
 
 
 def sumsq_f32(g, out):

@@ -249,22 +249,31 @@ def test_adamw_and_sumsq(K):
     n = 64 * 1000
     p, g = rnd(n, seed=50), rnd(n, seed=51) * 0.01
     m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
-    pb = torch.zeros(n, dtype=bf16, device="cuda")
-    seg_end = [64 * 300, n]
+    pb = p.to(bf16)
+    cut, frozen0 = 64 * 300, 64 * 900
+    cg = torch.zeros(n // 64, dtype=torch.uint8)
+    cg[300:900] = 1
+    cg[900:] = 255                                   # frozen tail
+    cg = cg.cuda()
     hp = torch.tensor([1e-3, 0.0, 5e-4, 0.05], device="cuda")
-    P = [p.cpu()[:seg_end[0]].clone(), p.cpu()[seg_end[0]:].clone()]
-    G = [g.cpu()[:seg_end[0]].clone(), g.cpu()[seg_end[0]:].clone()]
+    P = [p.cpu()[:cut].clone(), p.cpu()[cut:frozen0].clone()]
+    G = [g.cpu()[:cut].clone(), g.cpu()[cut:frozen0].clone()]
     Mo, Vo = [torch.zeros_like(x) for x in P], [torch.zeros_like(x) for x in P]
     ss = torch.zeros(1, device="cuda")
     K.sumsq_f32(g, ss)
     close(ss, (g.double() ** 2).sum().float().reshape(1), 1e-5, 0, "sumsq")
+    p_frozen = p[frozen0:].clone()
     b1, b2 = 0.9, 0.95
     for step in (1, 2, 3):
-        scal = torch.tensor([b1 ** step, b2 ** step, 1.0, 0.0], device="cuda")
-        gk = g.clone()
-        K.adamw_step(p, gk, m, v, pb, seg_end, hp, scal, b1, b2, 1e-8, True)
+        scal = torch.tensor([b1 ** step, b2 ** step, 0.5, 0.0], device="cuda")
+        gk = g.clone() * 2                           # grad_scale 0.5 undoes the x2
+        ss2 = torch.zeros(1, device="cuda")
+        K.adamw_step(p, gk, m, v, pb, cg, hp, scal, b1, b2, 1e-8, True, ss2)
         assert float(gk.abs().max()) == 0
+        close(ss2, (g[:frozen0].double() ** 2).sum().float().reshape(1), 1e-4, 0, "fused grad-norm^2")
         for s_, (lr, wd) in enumerate(((1e-3, 0.0), (5e-4, 0.05))):
             oracle_adamw(P[s_], G[s_], Mo[s_], Vo[s_], step, lr, b1, b2, 1e-8, wd)
-    close(p, torch.cat(P), 1e-5, 1e-6, "adamw p"); close(m, torch.cat(Mo), 1e-5, 1e-8, "adamw m"); close(v, torch.cat(Vo), 1e-5, 1e-10, "adamw v")
+    close(p[:frozen0], torch.cat(P), 1e-5, 1e-6, "adamw p"); close(m[:frozen0], torch.cat(Mo), 1e-5, 1e-8, "adamw m")
+    close(v[:frozen0], torch.cat(Vo), 1e-5, 1e-10, "adamw v")
+    assert torch.equal(p[frozen0:], p_frozen) and float(m[frozen0:].abs().max()) == 0
     assert torch.equal(pb.cpu(), p.cpu().to(bf16))
