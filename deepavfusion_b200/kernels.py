@@ -182,6 +182,9 @@ def layernorm_bwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor,
 # --------------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------------
+GEMM_TRACE = None     # bench.py sets this to a list to record the (M, N, K, majors, epilogue) of every launch
+
+
 def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
          bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
          res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
@@ -235,6 +238,10 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
     if window is not None:
         ga.g, ga.G, ga.off = window
     ga.split_k = split_k
+    if GEMM_TRACE is not None:
+        GEMM_TRACE.append(dict(M=M, N=N, K=K, a_kmajor=a_kmajor, b_kmajor=b_kmajor, lda=a.stride(0), ldb=b.stride(0),
+                               bias=bias is not None, act=act, aux=want_aux, res=res is not None, res_idx=res_idx is not None,
+                               out_bf16=out.dtype == torch.bfloat16, accumulate=accumulate, window=window, ldo=out.stride(-2)))
     check(_cabi.lib().davf_gemm(C.byref(ga), _stream()), "davf_gemm")
     return (out, aux) if want_aux else out
 

@@ -67,10 +67,11 @@ class FusedAdamW(torch.optim.Optimizer):
         self.scal[2] = scale
 
     @torch.no_grad()
-    def step(self, closure=None, zero_grad: bool = True):
+    def step(self, closure=None, zero_grad: bool = True, sync_hp: bool = True):
         """One fused launch: p, m, v update (+bf16 shadow, +grad-norm^2, +zero_grad)."""
         assert closure is None
-        self._sync_hp()
+        if sync_hp:
+            self._sync_hp()
         self.scal.mul_(self._beta_mul)                      # beta^t on the device
         self.grad_sumsq.zero_()
         b1, b2 = self.param_groups[0]["betas"]
