@@ -4,8 +4,8 @@
 // loop and no HBM round trip for the score matrix.  Strided q/k/v/o addressing lets the kernel read
 // packed qkv buffers, query sub-ranges (live rows only) and write packed dqkv buffers directly.
 //
-// Round-1 arithmetic runs on the CUDA cores in f32 (QK^T and PV are 3.4 % of the step's FLOPs,
-// SURVEY.md 7.3); the data path (bf16 I/O, f32 softmax statistics, saved log-sum-exp) is final.
+// This file is the CUDA-core (f32 FMA) CHECKER implementation, selected with davf_set_attn_impl(1);
+// the default path is the tensor-core kernel in attention_mma.cu.
 #include "common.cuh"
 
 namespace davf {
@@ -253,16 +253,15 @@ static bool strides_ok(int64_t rs, int64_t bs) { return rs % 4 == 0 && bs % 4 ==
 
 }  // namespace davf
 
-using namespace davf;
 
-extern "C" int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s) {
+namespace davf {
+int attn_simt_fwd(const davf_attn_fwd_args* a, cudaStream_t st) {
   DAVF_CHECK_ARG(a && a->q && a->k && a->v && a->o, "attention_fwd: null pointer");
   DAVF_CHECK_ARG(a->Nk > 0 && a->Nk <= kMaxKeys && a->Nq > 0 && a->H > 0 && a->B >= 0, "attention_fwd: Nq=%d Nk=%d (Nk <= %d)", a->Nq, a->Nk, kMaxKeys);
   DAVF_CHECK_ARG(strides_ok(a->q_rs, a->q_bs) && strides_ok(a->k_rs, a->k_bs) && strides_ok(a->v_rs, a->v_bs) && strides_ok(a->o_rs, a->o_bs),
                  "attention_fwd: strides must be multiples of 4 elements");
   DAVF_CHECK_ARG((((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v | (uintptr_t)a->o) & 7) == 0, "attention_fwd: pointers must be 8-byte aligned");
   if (a->B == 0) return DAVF_OK;
-  cudaStream_t st = as_stream(s);
   if (a->dqk == 64 && a->dv == 64) return launch_fwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_fwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_fwd<16, 64>(*a, st);
@@ -270,17 +269,17 @@ extern "C" int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s) 
   return DAVF_EUNSUPPORTED;
 }
 
-extern "C" int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s) {
+int attn_simt_bwd(const davf_attn_bwd_args* a, cudaStream_t st) {
   DAVF_CHECK_ARG(a && a->q && a->k && a->v && a->d_o && a->lse && a->dq && a->dk && a->dv_, "attention_bwd: null pointer");
   DAVF_CHECK_ARG(a->Nk > 0 && a->Nk <= kMaxKeys && a->Nq > 0 && a->Nq <= kMaxKeys, "attention_bwd: Nq=%d Nk=%d (<= %d)", a->Nq, a->Nk, kMaxKeys);
   DAVF_CHECK_ARG(strides_ok(a->q_rs, a->q_bs) && strides_ok(a->k_rs, a->k_bs) && strides_ok(a->v_rs, a->v_bs) &&
                      strides_ok(a->do_rs, a->do_bs) && strides_ok(a->dq_rs, a->dq_bs) && strides_ok(a->dk_rs, a->dk_bs) && strides_ok(a->dv_rs, a->dv_bs),
                  "attention_bwd: strides must be multiples of 4 elements");
   if (a->B == 0) return DAVF_OK;
-  cudaStream_t st = as_stream(s);
   if (a->dqk == 64 && a->dv == 64) return launch_bwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_bwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_bwd<16, 64>(*a, st);
   set_error("attention_bwd: head dims (%d,%d) unsupported", a->dqk, a->dv);
   return DAVF_EUNSUPPORTED;
 }
+}  // namespace davf

@@ -377,3 +377,7 @@ def launch_count() -> int:
 
 def set_gemm_impl(impl: int) -> None:
     check(_cabi.lib().davf_set_gemm_impl(impl), "davf_set_gemm_impl")
+
+
+def set_attn_impl(impl: int) -> None:
+    check(_cabi.lib().davf_set_attn_impl(impl), "davf_set_attn_impl")

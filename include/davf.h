@@ -41,6 +41,8 @@ int davf_device_sm(void);                     /* 100 for B200, <0 on error      
 /* 0 = tcgen05/TMA GEMM (default), 1 = SIMT checker GEMM (debug only; set by tests) */
 int davf_set_gemm_impl(int impl);
 int davf_get_gemm_impl(void);
+/* 0 = tensor-core attention (default), 1 = CUDA-core checker attention (debug only; set by tests) */
+int davf_set_attn_impl(int impl);
 /* Number of kernel launches issued by this library since process start (bench gpu_launches). */
 int64_t davf_launch_count(void);
 
@@ -153,7 +155,8 @@ int davf_gemm(const davf_gemm_args* a, davf_stream_t s);
  * query sub-ranges (live rows only) need no copies.
  * lse f32 [B,H,Nq] = log-sum-exp of the scaled logits (saved for backward).
  * accumulate != 0: o += result (used to add the two factorised pair attentions).
- * Supported (dqk, dv): (64,64), (32,32), (16,64).  Nk <= 256. */
+ * Supported (dqk, dv): (64,64), (32,32), (16,64).  Nk <= 256.  q / k / v rows must be 16-byte aligned
+ * (strides multiples of 8 elements). */
 typedef struct {
   const davf_bf16* q; int64_t q_bs; int64_t q_rs;
   const davf_bf16* k; int64_t k_bs; int64_t k_rs;

@@ -276,6 +276,10 @@ def set_gemm_impl(impl):
     pass
 
 
+def set_attn_impl(impl):
+    pass
+
+
 def install(monkeypatch=None):
     """Replace every kernel wrapper in deepavfusion_b200.kernels by its emulation."""
     import deepavfusion_b200.kernels as K

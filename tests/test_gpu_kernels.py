@@ -191,8 +191,18 @@ def test_gemm_all_modes(impl):
 
 # ---------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,Nq,Nk,dqk,dv,skip", [(4, 12, 49, 81, 64, 64, 32), (3, 16, 228, 228, 32, 32, 0), (5, 12, 16, 8, 16, 64, 0),
-                                                   (2, 12, 8, 19, 64, 64, 0), (2, 2, 4, 1, 64, 64, 0), (2, 12, 196, 228, 64, 64, 32)])
-def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip):
+                                                   (2, 12, 8, 19, 64, 64, 0), (2, 2, 4, 1, 64, 64, 0), (2, 12, 196, 228, 64, 64, 32),
+                                                   (2, 16, 128, 128, 32, 32, 0), (1, 2, 65, 129, 64, 64, 0)])
+@pytest.mark.parametrize("impl", [0, 1], ids=["mma", "simt"])
+def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
+    K.set_attn_impl(impl)
+    try:
+        _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
+    finally:
+        K.set_attn_impl(0)
+
+
+def _attention_case(K, B, H, Nq, Nk, dqk, dv, skip):
     scale = 0.125
     if dqk == dv and Nq + skip <= Nk:       # packed qkv buffer with a dead query prefix, like the encoder blocks
         S = Nk
