@@ -31,6 +31,7 @@ extern "C" int davf_gemm(const davf_gemm_args* a, davf_stream_t s) {
   DAVF_CHECK_ARG(a->split_k <= 1 || a->accumulate, "gemm: split_k > 1 needs accumulate");
   DAVF_CHECK_ARG(!a->accumulate || (a->act == DAVF_ACT_NONE && !a->res && !a->aux_out), "gemm: accumulate excludes act / res / aux_out");
   DAVF_CHECK_ARG(a->g == 0 || (a->g > 0 && a->G >= a->g && a->off >= 0 && a->off + a->g <= a->G), "gemm: bad row window g=%d G=%d off=%d", a->g, a->G, a->off);
+  DAVF_CHECK_ARG(!a->rowsum_out || a->accumulate, "gemm: rowsum_out is only supported on accumulate (wgrad) launches");
   if (g_gemm_impl.load() == 1) return gemm_simt_launch(*a, as_stream(s));
   return gemm_tc_launch(*a, as_stream(s));
 }

@@ -20,6 +20,7 @@ struct EpiParams {
   int accumulate;
   int g, G, off;
   int64_t M, N;
+  float* rowsum_out;
 };
 
 static inline EpiParams make_epi(const davf_gemm_args& a) {
@@ -27,7 +28,7 @@ static inline EpiParams make_epi(const davf_gemm_args& a) {
   p.bias = a.bias; p.act = a.act; p.aux_out = a.aux_out; p.aux_in = a.aux_in; p.ldaux = a.ldaux;
   p.res = a.res; p.ldres = a.ldres; p.res_idx = a.res_idx; p.out = a.out; p.ldo = a.ldo;
   p.out_bf16 = a.out_bf16; p.accumulate = a.accumulate; p.g = a.g; p.G = a.G; p.off = a.off;
-  p.M = a.M; p.N = a.N;
+  p.M = a.M; p.N = a.N; p.rowsum_out = a.rowsum_out;
   return p;
 }
 
@@ -67,7 +68,7 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, int64_t m, int6
     }
     if (p.accumulate) {
       float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
-      atomicAdd(o + 0, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     } else if (p.out_bf16) {
       uint2 o;
       o.x = pack_bf16x2(v.x, v.y);

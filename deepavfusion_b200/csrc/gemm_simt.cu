@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const uint16_t* __restri
   int64_t ke = kb + k_chunk;
   if (ke > K) ke = K;
   float acc[4][4] = {};
+  float rs[4] = {};
   for (int64_t k0 = kb; k0 < ke; k0 += SK) {
     for (int i = threadIdx.x; i < ST * SK; i += 256) {
       int mm, kk;
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const uint16_t* __restri
     for (int kk = 0; kk < SK; ++kk) {
       float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; rs[i] += a[i]; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -49,6 +50,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const uint16_t* __restri
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) epilogue_row<4>(ep, m0 + ty * 4 + i, n0 + tx * 4, acc[i], blockIdx.z == 0);
+  if (ep.rowsum_out && blockIdx.x == 0 && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (m0 + ty * 4 + i < M) atomicAdd(ep.rowsum_out + m0 + ty * 4 + i, rs[i]);
+  }
 }
 
 int gemm_simt_launch(const davf_gemm_args& a, cudaStream_t st) {

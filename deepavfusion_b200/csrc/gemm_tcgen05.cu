@@ -3,7 +3,9 @@
 // specialised:
 //     warp 0      TMA producer            (one elected lane)
 //     warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / commit)
-//     warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> fused epilogue -> global
+//     warps 2..9  epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns):
+//                 tcgen05.ld TMEM -> registers -> per-warp smem staging (transposes "one row per lane"
+//                 into "4 lanes per row") -> fused epilogue with fully coalesced global loads / stores
 // Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a double-buffered TMEM accumulator
 // (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -29,7 +31,12 @@ namespace davf {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
+constexpr int kStageCols = 16;                         // columns per epilogue chunk
+constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
+constexpr uint32_t kStagingBytes = kNumEpiWarps * 32 * kStagePitch * 4;
+constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
 constexpr uint64_t kSpinLimit = 4000000000ull;   // ~2 s of SM clocks: trap instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------
@@ -98,6 +105,25 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor (sm_100 format: version = 1 at bit 46, layout type at [61,64))
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -140,12 +166,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;            // two accumulator stages (power of two: 256 / 512)
+  constexpr uint32_t TMEM_COLS = 512;               // two accumulator stages of BN columns (+ 2 x 16 row-sum columns when BN = 128)
   constexpr uint32_t IDESC = make_idesc(BM, BN, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1);
+  constexpr uint32_t IDESC_ONES = make_idesc(BM, 16, A_KMAJOR ? 0 : 1, 0);
+  constexpr uint32_t ROWSUM_COL = 2 * BN;           // only used when BN == 128 (host enforces it)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
+  const uint32_t ones_base = stage_base + kStagingBytes;                  // 1024-byte aligned, kOnesBytes
+  const uint32_t bar_base = ones_base + kOnesBytes;
+  const bool want_rowsum = ep.rowsum_out != nullptr;
   // barrier addresses: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -164,9 +195,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kNumEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (want_rowsum) {      // bf16 1.0 everywhere: layout-agnostic B operand
+    for (uint32_t i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(ones_base + 4 * i), "r"(0x3F803F80u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
@@ -223,6 +259,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const bool rowsum_tile = want_rowsum && n_blk == 0;
+        const uint64_t ones_desc = make_smem_desc(ones_base, 16, 1024);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -235,6 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
                                             : make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024);
             umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
+              umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -244,7 +284,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3;
+    const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns
+    float* stg = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 32 * kStagePitch;
+    const int rr = lane >> 2, cc = (lane & 3) * 4;   // coalesced phase: 4 lanes per row, 8 rows per iteration
     int local = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       int m_blk, n_blk, sp, kb0, kb1;
@@ -253,17 +296,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t acc_phase = (local >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t m = (int64_t)m_blk * BM + quad * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float z[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        tmem_ld_32x32b_x32(taddr, z);
-        epilogue_row<32>(ep, m, (int64_t)n_blk * BN + c * 32, z, sp == 0);
+      const int64_t m_base = (int64_t)m_blk * BM + quad * 32;
+      if (want_rowsum && n_blk == 0 && half == 0) {
+        const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
+        if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / kStageCols; ++c) {
+        const int col0 = half * (BN / 2) + c * kStageCols;
+        float z[kStageCols];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), z);
+        if (c == BN / 2 / kStageCols - 1) {    // accumulator fully read: hand the TMEM stage back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int j = 0; j < kStageCols; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+        __syncwarp();
+        const int64_t n = (int64_t)n_blk * BN + col0 + cc;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + rr;
+          float v4[4];
+          *reinterpret_cast<float4*>(v4) = *reinterpret_cast<const float4*>(stg + r * kStagePitch + cc);
+          epilogue_row<4>(ep, m_base + r, n, v4, sp == 0);
+        }
+        __syncwarp();
+      }
     }
   }
 
@@ -349,7 +410,8 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
 
 template <int BN, int STAGES, bool AK, bool BKM>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 4) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + kStagingBytes + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
+  static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM>;
   if (!attr_set) {
@@ -377,7 +439,7 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   // the problem still yields at least ~one full wave of CTAs, otherwise 128 for parallelism.
   const int64_t m_tiles = (a.M + BM - 1) / BM;
   int bn = 128;
-  if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs) bn = 256;
+  if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs && !a.rowsum_out) bn = 256;   // row-sum columns need BN = 128
   const int64_t n_tiles = (a.N + bn - 1) / bn;
   const int kb_total = (int)((a.K + BK - 1) / BK);
   int splits = a.split_k;

@@ -41,9 +41,10 @@ def linear_bwd(st: ParamStore, dy: Tensor, x: Tensor, W: nn.Parameter, b: Option
                need_dx: bool = True, **epi):
     """Accumulates dW (+= dy^T x) and db (+= colsum dy) into the flat gradient buffer and returns
     dx = dy W[:, cols] (with optional fused epilogue) or None."""
-    if W.requires_grad:
-        K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True)
-    if b is not None and b.requires_grad:
+    want_b = b is not None and b.requires_grad
+    if W.requires_grad:       # bias gradient rides along in the wgrad launch (ones-tile MMA)
+        K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True, rowsum_out=st.grad(b) if want_b else None)
+    elif want_b:
         K.colsum_bf16(dy, st.grad(b))
     if not need_dx:
         return None

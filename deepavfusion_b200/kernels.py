@@ -189,7 +189,7 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
          bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
          res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
          out: Optional[Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False,
-         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0):
+         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0, rowsum_out: Optional[Tensor] = None):
     """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of davf.h.
 
     ``a`` / ``b`` are the STORED 2-D bf16 matrices (row-major views, stride(1) == 1):
@@ -238,10 +238,14 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
     if window is not None:
         ga.g, ga.G, ga.off = window
     ga.split_k = split_k
+    if rowsum_out is not None:
+        ga.rowsum_out = _need(rowsum_out, torch.float32, "rowsum_out").data_ptr()
+        assert rowsum_out.numel() == M
     if GEMM_TRACE is not None:
         GEMM_TRACE.append(dict(M=M, N=N, K=K, a_kmajor=a_kmajor, b_kmajor=b_kmajor, lda=a.stride(0), ldb=b.stride(0),
                                bias=bias is not None, act=act, aux=want_aux, res=res is not None, res_idx=res_idx is not None,
-                               out_bf16=out.dtype == torch.bfloat16, accumulate=accumulate, window=window, ldo=out.stride(-2)))
+                               out_bf16=out.dtype == torch.bfloat16, accumulate=accumulate, window=window, ldo=out.stride(-2),
+                               rowsum=rowsum_out is not None))
     check(_cabi.lib().davf_gemm(C.byref(ga), _stream()), "davf_gemm")
     return (out, aux) if want_aux else out
 

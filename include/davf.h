@@ -130,6 +130,9 @@ int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s);
  *   out[row(m)*ldo + n] = z   as f32 / bf16,  or atomically += z (f32) when accumulate != 0
  * split_k > 1 requires accumulate (partial sums are reduced by f32 atomics; bias is added by
  * split 0 only).
+ *   rowsum_out[m] += sum_k A(m,k)   (if rowsum_out; f32 [M], atomic).  This is the bias gradient of a
+ * wgrad launch (A = dy^T): the tensor core computes it with one extra N=16 MMA per k-step against a
+ * constant all-ones B tile, so no separate column-sum pass over dy is needed.
  */
 enum { DAVF_ACT_NONE = 0, DAVF_ACT_GELU = 1, DAVF_ACT_DGELU = 2 };
 typedef struct {
@@ -143,6 +146,7 @@ typedef struct {
   void* out; int64_t ldo; int out_bf16; int accumulate;
   int g; int G; int off;
   int split_k;
+  float* rowsum_out;
 } davf_gemm_args;
 int davf_gemm(const davf_gemm_args* a, davf_stream_t s);
 

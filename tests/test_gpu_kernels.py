@@ -143,8 +143,10 @@ for (M, N, Kd) in shapes:
     check(f'dgrad K,MN {{M}}x{{Kd}}x{{N}}', K.gemm(dy, b, True, False, out_dtype=torch.float32), dy.float() @ b.float(), 1e-2, 1e-1 * (N / 768) ** 0.5)
     # wgrad: both MN-major, accumulate with auto split-K
     out = torch.ones(N, Kd, device='cuda')
-    K.gemm(dy, a, False, False, out=out, accumulate=True)
+    db = torch.ones(N, device='cuda')
+    K.gemm(dy, a, False, False, out=out, accumulate=True, rowsum_out=db)
     check(f'wgrad MN,MN {{N}}x{{Kd}}x{{M}}', out, 1 + dy.float().t() @ a.float(), 1e-2, 1e-1 * (M / 768) ** 0.5)
+    check(f'wgrad bias (ones-tile MMA) {{N}}x{{M}}', db, 1 + dy.float().sum(0), 1e-2, 2e-2 * (M / 768) ** 0.5)
 # epilogues
 M, N, Kd = 392, 3072, 768
 a, b = rnd(M, Kd, seed=4, dtype=bf16), rnd(N, Kd, seed=5, dtype=bf16) * 0.05
