@@ -48,7 +48,7 @@ class GemmArgs(C.Structure):
                 ("res", vp), ("ldres", C.c_int64), ("res_idx", vp),
                 ("out", vp), ("ldo", C.c_int64), ("out_bf16", C.c_int), ("accumulate", C.c_int),
                 ("g", C.c_int), ("G", C.c_int), ("off", C.c_int),
-                ("split_k", C.c_int), ("rowsum_out", vp)]
+                ("split_k", C.c_int), ("rowsum_out", vp), ("debug_clocks", vp)]
 
 
 class AttnFwdArgs(C.Structure):

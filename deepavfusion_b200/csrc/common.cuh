@@ -64,25 +64,34 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-// erf to 1.5e-7 absolute error (Abramowitz & Stegun 7.1.26) with two MUFU ops (rcp, ex2): ~14
-// instructions instead of ~25 for erff().  Its consumers round to bf16 (8 mantissa bits), so the
-// result is indistinguishable from the exact-erf GELU of torch nn.GELU() / timm Mlp.
-__device__ __forceinline__ float erf_fast(float x) {
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Gaussian CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and e = exp(-x^2 / 2), from the Abramowitz & Stegun
+// 7.1.26 rational form of erf (|error| <= 1.5e-7) with two MUFU ops (rcp, ex2): ~15 instructions
+// instead of ~30 for erff() + expf().  Every consumer rounds to bf16 (8 mantissa bits), so GELU and
+// its derivative are indistinguishable from the exact-erf torch nn.GELU() / timm Mlp activation.
+__device__ __forceinline__ void gauss_terms(float x, float& cdf, float& e) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p * t, e, 1.0f), x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  e = ex2_approx(-0.72134752044448170f * x * x);
+  const float h = p * t * e;                   // 0.5 * erfc(|x| / sqrt 2)
+  cdf = x >= 0.f ? 1.0f - h : h;
 }
 // (erf) GELU and its derivative -- torch nn.GELU() default, timm Mlp act_layer.
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, e;
+  gauss_terms(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * exp2f(-0.72134752044448170f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gauss_terms(x, cdf, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 // block-wide sum for blockDim.x <= 1024 (multiple of 32); scratch >= 32 floats

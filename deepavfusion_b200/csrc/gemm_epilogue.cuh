@@ -21,6 +21,7 @@ struct EpiParams {
   int g, G, off;
   int64_t M, N;
   float* rowsum_out;
+  long long* debug_clocks;
 };
 
 static inline EpiParams make_epi(const davf_gemm_args& a) {
@@ -29,6 +30,7 @@ static inline EpiParams make_epi(const davf_gemm_args& a) {
   p.res = a.res; p.ldres = a.ldres; p.res_idx = a.res_idx; p.out = a.out; p.ldo = a.ldo;
   p.out_bf16 = a.out_bf16; p.accumulate = a.accumulate; p.g = a.g; p.G = a.G; p.off = a.off;
   p.M = a.M; p.N = a.N; p.rowsum_out = a.rowsum_out;
+  p.debug_clocks = reinterpret_cast<long long*>(a.debug_clocks);
   return p;
 }
 

@@ -215,6 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
   const int num_tiles = ts.num_tiles();
+  long long* dbg = (ep.debug_clocks && blockIdx.x == 0) ? ep.debug_clocks : nullptr;   // optional timeline probe of CTA 0
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -226,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (dbg && t == 0 && kb == kb0) dbg[1] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -264,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (dbg && t == 0 && kb == kb0) dbg[2] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -280,33 +284,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        if (dbg && t == 0) dbg[3] = clock64();
       }
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
+    // Per 16-column chunk: TMEM -> registers (one row per lane) -> per-warp smem staging -> "4 lanes per
+    // row" so that every global access is a fully used 32/64-byte row segment.  The global operands of
+    // the fused epilogue (bias, residual, pre-activation) for chunk c+1 are loaded into registers while
+    // chunk c is processed (and for the first chunk before the accumulator is even ready), so their
+    // L2/HBM latency is off the critical path of this 10-warp, low-occupancy CTA.
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
     const int half = (warp - 2) >> 2;          // which half of the tile's columns
     float* stg = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 32 * kStagePitch;
     const int rr = lane >> 2, cc = (lane & 3) * 4;   // coalesced phase: 4 lanes per row, 8 rows per iteration
+    constexpr int NCHUNK = BN / 2 / kStageCols;
+    const bool has_bias = ep.bias != nullptr, has_res = ep.res != nullptr, has_auxin = ep.act == DAVF_ACT_DGELU;
+    struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
     int local = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
       int m_blk, n_blk, sp, kb0, kb1;
       ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1u;
+      const int64_t m_base = (int64_t)m_blk * BM + quad * 32;
+      // per-tile row bookkeeping for the 4 rows this lane touches in the coalesced phase
+      int64_t out_off[4], res_off[4], aux_off[4];
+      bool rvalid[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int64_t m = m_base + it * 8 + rr;
+        rvalid[it] = m < ep.M;
+        const int64_t mm = rvalid[it] ? m : 0;
+        const int64_t orow = ep.g > 0 ? (mm / ep.g) * (int64_t)ep.G + ep.off + (mm % ep.g) : mm;
+        out_off[it] = orow * ep.ldo;
+        res_off[it] = has_res ? (ep.res_idx ? ep.res_idx[mm] : orow) * ep.ldres : 0;
+        aux_off[it] = mm * ep.ldaux;
+      }
+      const bool add_bias = has_bias && sp == 0;
+      auto prefetch = [&](int c, Pre& pr) {
+        const int64_t n = (int64_t)n_blk * BN + half * (BN / 2) + c * kStageCols + cc;
+        const bool nv = n < ep.N;
+        pr.bias = (add_bias && nv) ? *reinterpret_cast<const float4*>(ep.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const bool ok = nv && rvalid[it];
+          pr.res[it] = (has_res && ok) ? *reinterpret_cast<const float4*>(ep.res + res_off[it] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pr.aux[it] = (has_auxin && ok) ? *reinterpret_cast<const uint2*>(ep.aux_in + aux_off[it] + n) : make_uint2(0u, 0u);
+        }
+      };
+      Pre cur, nxt;
+      prefetch(0, cur);                       // in flight while the MMAs of this tile still run
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t m_base = (int64_t)m_blk * BM + quad * 32;
+      if (dbg && t == 0 && warp == 2 && lane == 0) dbg[4] = clock64();
       if (want_rowsum && n_blk == 0 && half == 0) {
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 2 / kStageCols; ++c) {
+      for (int c = 0; c < NCHUNK; ++c) {          // not unrolled: 16 inlined GELUs per chunk already fill the L0 I-cache
         const int col0 = half * (BN / 2) + c * kStageCols;
         float z[kStageCols];
         tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), z);
-        if (c == BN / 2 / kStageCols - 1) {    // accumulator fully read: hand the TMEM stage back to the MMA warp early
+        if (c == NCHUNK - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -315,21 +356,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < kStageCols; j += 4)
           *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
         __syncwarp();
+        if (c + 1 < NCHUNK) prefetch(c + 1, nxt);
         const int64_t n = (int64_t)n_blk * BN + col0 + cc;
+        if (n < ep.N) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 8 + rr;
-          float v4[4];
-          *reinterpret_cast<float4*>(v4) = *reinterpret_cast<const float4*>(stg + r * kStagePitch + cc);
-          epilogue_row<4>(ep, m_base + r, n, v4, sp == 0);
+          for (int it = 0; it < 4; ++it) {
+            if (!rvalid[it]) continue;
+            float4 v = *reinterpret_cast<const float4*>(stg + (it * 8 + rr) * kStagePitch + cc);
+            v.x += cur.bias.x; v.y += cur.bias.y; v.z += cur.bias.z; v.w += cur.bias.w;
+            if (ep.aux_out) {
+              uint2 o;
+              o.x = pack_bf16x2(v.x, v.y);
+              o.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(ep.aux_out + aux_off[it] + n) = o;
+            }
+            if (ep.act == DAVF_ACT_GELU) {
+              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            } else if (has_auxin) {
+              const float2 lo = unpack_bf16x2(cur.aux[it].x), hi = unpack_bf16x2(cur.aux[it].y);
+              v.x *= dgelu_erf(lo.x); v.y *= dgelu_erf(lo.y); v.z *= dgelu_erf(hi.x); v.w *= dgelu_erf(hi.y);
+            }
+            v.x += cur.res[it].x; v.y += cur.res[it].y; v.z += cur.res[it].z; v.w += cur.res[it].w;
+            if (ep.accumulate) {
+              float* o = reinterpret_cast<float*>(ep.out) + out_off[it] + n;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            } else if (ep.out_bf16) {
+              uint2 o;
+              o.x = pack_bf16x2(v.x, v.y);
+              o.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out) + out_off[it] + n) = o;
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + out_off[it] + n) = v;
+            }
+          }
         }
         __syncwarp();
+        cur = nxt;
       }
+      if (dbg && t == 0 && warp == 2 && lane == 0) dbg[5] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

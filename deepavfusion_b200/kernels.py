@@ -189,7 +189,8 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
          bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
          res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
          out: Optional[Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False,
-         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0, rowsum_out: Optional[Tensor] = None):
+         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0, rowsum_out: Optional[Tensor] = None,
+         debug_clocks: Optional[Tensor] = None):
     """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of davf.h.
 
     ``a`` / ``b`` are the STORED 2-D bf16 matrices (row-major views, stride(1) == 1):
@@ -241,6 +242,8 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
     if rowsum_out is not None:
         ga.rowsum_out = _need(rowsum_out, torch.float32, "rowsum_out").data_ptr()
         assert rowsum_out.numel() == M
+    if debug_clocks is not None:
+        ga.debug_clocks = _need(debug_clocks, torch.int64, "debug_clocks").data_ptr()
     if GEMM_TRACE is not None:
         GEMM_TRACE.append(dict(M=M, N=N, K=K, a_kmajor=a_kmajor, b_kmajor=b_kmajor, lda=a.stride(0), ldb=b.stride(0),
                                bias=bias is not None, act=act, aux=want_aux, res=res is not None, res_idx=res_idx is not None,

@@ -147,6 +147,7 @@ typedef struct {
   int g; int G; int off;
   int split_k;
   float* rowsum_out;
+  int64_t* debug_clocks;   /* optional: 8 x i64 SM-clock timeline of CTA 0 (profiling aid), else NULL */
 } davf_gemm_args;
 int davf_gemm(const davf_gemm_args* a, davf_stream_t s);
 

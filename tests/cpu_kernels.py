@@ -142,7 +142,7 @@ def _dgelu(x):
 
 
 def gemm(a, b, a_kmajor=True, b_kmajor=True, *, bias=None, act=ACT_NONE, want_aux=False, aux_in=None, res=None,
-         res_idx=None, out=None, out_dtype=torch.bfloat16, accumulate=False, window=None, split_k=0, rowsum_out=None):
+         res_idx=None, out=None, out_dtype=torch.bfloat16, accumulate=False, window=None, split_k=0, rowsum_out=None, debug_clocks=None):
     A = a.float() if a_kmajor else a.float().t()
     if rowsum_out is not None:
         rowsum_out += A.sum(1)
