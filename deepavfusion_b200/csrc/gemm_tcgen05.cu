@@ -159,7 +159,25 @@ struct TileSched {
   }
 };
 
-template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+// Compile-time epilogue specialisation.  EPI < 0: every option is a run-time flag (rare shapes: row
+// windows, gathered residuals, ...).  EPI >= 0: bit mask of the options below, fixed at compile time
+// for the six epilogues that carry > 90 % of the GEMM time, so that no flag tests, dead operand
+// prefetches or dead address arithmetic remain in the (instruction-bound) epilogue loop.
+enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_AUX = 8, EPI_RES = 16, EPI_BF16 = 32, EPI_RED = 64 };
+template <int EPI>
+struct EpiSel {
+  static constexpr bool kStatic = EPI >= 0;
+  __device__ __forceinline__ static bool bias(const EpiParams& p) { return kStatic ? (EPI & EPI_BIAS) != 0 : p.bias != nullptr; }
+  __device__ __forceinline__ static bool gelu(const EpiParams& p) { return kStatic ? (EPI & EPI_GELU) != 0 : p.act == DAVF_ACT_GELU; }
+  __device__ __forceinline__ static bool dgelu(const EpiParams& p) { return kStatic ? (EPI & EPI_DGELU) != 0 : p.act == DAVF_ACT_DGELU; }
+  __device__ __forceinline__ static bool aux(const EpiParams& p) { return kStatic ? (EPI & EPI_AUX) != 0 : p.aux_out != nullptr; }
+  __device__ __forceinline__ static bool res(const EpiParams& p) { return kStatic ? (EPI & EPI_RES) != 0 : p.res != nullptr; }
+  __device__ __forceinline__ static bool bf16(const EpiParams& p) { return kStatic ? (EPI & EPI_BF16) != 0 : p.out_bf16 != 0; }
+  __device__ __forceinline__ static bool red(const EpiParams& p) { return kStatic ? (EPI & EPI_RED) != 0 : p.accumulate != 0; }
+  __device__ __forceinline__ static bool remap(const EpiParams& p) { return kStatic ? false : (p.g > 0 || p.res_idx != nullptr); }
+};
+
+template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                TileSched ts, EpiParams ep) {
@@ -299,7 +317,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* stg = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 32 * kStagePitch;
     const int rr = lane >> 2, cc = (lane & 3) * 4;   // coalesced phase: 4 lanes per row, 8 rows per iteration
     constexpr int NCHUNK = BN / 2 / kStageCols;
-    const bool has_bias = ep.bias != nullptr, has_res = ep.res != nullptr, has_auxin = ep.act == DAVF_ACT_DGELU;
+    using F = EpiSel<EPI>;
+    const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
     struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
     int local = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
@@ -316,10 +335,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int64_t m = m_base + it * 8 + rr;
         rvalid[it] = m < ep.M;
         const int64_t mm = rvalid[it] ? m : 0;
-        const int64_t orow = ep.g > 0 ? (mm / ep.g) * (int64_t)ep.G + ep.off + (mm % ep.g) : mm;
+        int64_t orow = mm, rrow = mm;
+        if (F::remap(ep)) {
+          if (ep.g > 0) orow = (mm / ep.g) * (int64_t)ep.G + ep.off + (mm % ep.g);
+          rrow = (has_res && ep.res_idx) ? ep.res_idx[mm] : orow;
+        }
         out_off[it] = orow * ep.ldo;
-        res_off[it] = has_res ? (ep.res_idx ? ep.res_idx[mm] : orow) * ep.ldres : 0;
-        aux_off[it] = mm * ep.ldaux;
+        res_off[it] = has_res ? rrow * ep.ldres : 0;
+        aux_off[it] = (F::aux(ep) || has_auxin) ? mm * ep.ldaux : 0;
       }
       const bool add_bias = has_bias && sp == 0;
       auto prefetch = [&](int c, Pre& pr) {
@@ -342,8 +365,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
-#pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {          // not unrolled: 16 inlined GELUs per chunk already fill the L0 I-cache
+      // One chunk: `use` holds this chunk's prefetched operands, `fill` receives the next chunk's.  The loop
+      // below is unrolled by two with the buffers swapped, so no register copies (which would force a wait on
+      // the in-flight loads) sit between chunks.
+      auto process = [&](int c, const Pre& use, Pre& fill) {
         const int col0 = half * (BN / 2) + c * kStageCols;
         float z[kStageCols];
         tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), z);
@@ -356,31 +381,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < kStageCols; j += 4)
           *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
         __syncwarp();
-        if (c + 1 < NCHUNK) prefetch(c + 1, nxt);
+        if (c + 1 < NCHUNK) prefetch(c + 1, fill);
         const int64_t n = (int64_t)n_blk * BN + col0 + cc;
         if (n < ep.N) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             if (!rvalid[it]) continue;
             float4 v = *reinterpret_cast<const float4*>(stg + (it * 8 + rr) * kStagePitch + cc);
-            v.x += cur.bias.x; v.y += cur.bias.y; v.z += cur.bias.z; v.w += cur.bias.w;
-            if (ep.aux_out) {
+            if (has_bias) { v.x += use.bias.x; v.y += use.bias.y; v.z += use.bias.z; v.w += use.bias.w; }
+            if (F::aux(ep)) {
               uint2 o;
               o.x = pack_bf16x2(v.x, v.y);
               o.y = pack_bf16x2(v.z, v.w);
               *reinterpret_cast<uint2*>(ep.aux_out + aux_off[it] + n) = o;
             }
-            if (ep.act == DAVF_ACT_GELU) {
+            if (F::gelu(ep)) {
               v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
             } else if (has_auxin) {
-              const float2 lo = unpack_bf16x2(cur.aux[it].x), hi = unpack_bf16x2(cur.aux[it].y);
+              const float2 lo = unpack_bf16x2(use.aux[it].x), hi = unpack_bf16x2(use.aux[it].y);
               v.x *= dgelu_erf(lo.x); v.y *= dgelu_erf(lo.y); v.z *= dgelu_erf(hi.x); v.w *= dgelu_erf(hi.y);
             }
-            v.x += cur.res[it].x; v.y += cur.res[it].y; v.z += cur.res[it].z; v.w += cur.res[it].w;
-            if (ep.accumulate) {
+            if (has_res) { v.x += use.res[it].x; v.y += use.res[it].y; v.z += use.res[it].z; v.w += use.res[it].w; }
+            if (F::red(ep)) {
               float* o = reinterpret_cast<float*>(ep.out) + out_off[it] + n;
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-            } else if (ep.out_bf16) {
+            } else if (F::bf16(ep)) {
               uint2 o;
               o.x = pack_bf16x2(v.x, v.y);
               o.y = pack_bf16x2(v.z, v.w);
@@ -391,12 +416,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         __syncwarp();
-        cur = nxt;
+      };
+      static_assert(NCHUNK % 2 == 0, "chunk loop is unrolled by two");
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; c += 2) {
+        process(c, cur, nxt);
+        process(c + 1, nxt, cur);
       }
       if (dbg && t == 0 && warp == 2 && lane == 0) dbg[5] = clock64();
     }
   }
 
+  __syncwarp();          // lanes 1..31 of the producer / MMA warps skipped the role loops: reconverge, so that the
+                         // aligned barrier below is executed once per warp (a divergent bar.sync counts a warp twice)
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[6] = clock64();
@@ -478,12 +510,12 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
-template <int BN, int STAGES, bool AK, bool BKM>
+template <int BN, int STAGES, bool AK, bool BKM, int EPI>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + kStagingBytes + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM>;
+  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI>;
   if (!attr_set) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -495,13 +527,40 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
   return DAVF_OK;
 }
 
+// run-time epilogue mask of a launch, or -1 if it needs the generic kernel
+static int epi_mask(const davf_gemm_args& a) {
+  if (a.g > 0 || a.res_idx || a.rowsum_out || a.debug_clocks) return -1;
+  int m = 0;
+  if (a.bias) m |= EPI_BIAS;
+  if (a.act == DAVF_ACT_GELU) m |= EPI_GELU;
+  if (a.act == DAVF_ACT_DGELU) m |= EPI_DGELU;
+  if (a.aux_out) m |= EPI_AUX;
+  if (a.res) m |= EPI_RES;
+  if (a.out_bf16) m |= EPI_BF16;
+  if (a.accumulate) m |= EPI_RED;
+  return m;
+}
+
 template <int BN, int STAGES>
 static int launch_major(const davf_gemm_args& a, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, cudaStream_t st) {
   const EpiParams ep = make_epi(a);
-  if (a.a_kmajor && a.b_kmajor) return launch_cfg<BN, STAGES, true, true>(ta, tb, ts, ep, st);
-  if (a.a_kmajor && !a.b_kmajor) return launch_cfg<BN, STAGES, true, false>(ta, tb, ts, ep, st);
-  if (!a.a_kmajor && !a.b_kmajor) return launch_cfg<BN, STAGES, false, false>(ta, tb, ts, ep, st);
-  return launch_cfg<BN, STAGES, false, true>(ta, tb, ts, ep, st);
+  const int em = epi_mask(a);
+  if (a.a_kmajor && a.b_kmajor) {            // forward
+    if (em == (EPI_BIAS | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_BF16>(ta, tb, ts, ep, st);
+    if (em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16>(ta, tb, ts, ep, st);
+    if (em == (EPI_BIAS | EPI_RES)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_RES>(ta, tb, ts, ep, st);
+    return launch_cfg<BN, STAGES, true, true, -1>(ta, tb, ts, ep, st);
+  }
+  if (a.a_kmajor && !a.b_kmajor) {           // dgrad
+    if (em == EPI_BF16) return launch_cfg<BN, STAGES, true, false, EPI_BF16>(ta, tb, ts, ep, st);
+    if (em == (EPI_DGELU | EPI_BF16)) return launch_cfg<BN, STAGES, true, false, EPI_DGELU | EPI_BF16>(ta, tb, ts, ep, st);
+    return launch_cfg<BN, STAGES, true, false, -1>(ta, tb, ts, ep, st);
+  }
+  if (!a.a_kmajor && !a.b_kmajor) {          // wgrad (row-sum launches take the generic kernel)
+    if (em == EPI_RED) return launch_cfg<BN, STAGES, false, false, EPI_RED>(ta, tb, ts, ep, st);
+    return launch_cfg<BN, STAGES, false, false, -1>(ta, tb, ts, ep, st);
+  }
+  return launch_cfg<BN, STAGES, false, true, -1>(ta, tb, ts, ep, st);
 }
 
 int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
