@@ -106,6 +106,31 @@ class PatchEmbedFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# a5  fusion tokens broadcast over the batch (deepavfusion.py:97): backward = batch sum
+# --------------------------------------------------------------------------------------------
+class BroadcastTokensFn(torch.autograd.Function):
+    """``fusion_tokens.expand(B, -1, -1)`` with the gradient reduced by our kernel straight into the flat
+    gradient buffer, so that NO parameter gradient travels through autograd ``AccumulateGrad`` nodes
+    (those pin the stream they were first created on, which breaks multi-stream CUDA-graph capture)."""
+
+    @staticmethod
+    def forward(ctx, tokens: Tensor, B: int, m: SimpleNamespace):
+        ctx.m = m
+        return tokens.detach().expand(B, -1, -1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dx: Tensor):
+        m = ctx.m
+        st: ParamStore = m.store
+        dx = dx.contiguous()
+        _, F, D = dx.shape
+        if m.tokens.requires_grad:
+            K.batchsum_f32(dx, 0, F, st.grad(m.tokens).view(F, D), True)
+        _done(m)
+        return None, None, None
+
+
+# --------------------------------------------------------------------------------------------
 # a3  attention half of a timm Block:  y = x + proj(attn(qkv(LN(cat(xp, x)))))  on the live rows
 # --------------------------------------------------------------------------------------------
 class AttnBranchFn(torch.autograd.Function):

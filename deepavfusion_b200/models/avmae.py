@@ -8,6 +8,7 @@ decoder is built (``decoder_arch: plain`` in every config; the Swin decoder is o
 """
 from __future__ import annotations
 
+import contextlib
 from types import SimpleNamespace
 
 import torch
@@ -131,11 +132,19 @@ class AVMAE(nn.Module):
 
         x_image, x_audio, x_fusion = self.encoder(image, audio, image_ids_keep=image_ids_keep, audio_ids_keep=audio_ids_keep)
 
+        # the two decoders are independent: issue the audio decoder on a side stream (see DeepAVFusion._side_streams)
+        side = self.encoder._side_streams(device)
+        cur = torch.cuda.current_stream() if side else None
+        if side:
+            side[0].wait_stream(cur)
         seq_i = self.forward_decoder(x_image, x_fusion, image_ids_restore, "image", image_ids_keep)
         hi = self._dec["image"][1]
         loss_image, pred_image = Fn.PredLossFn.apply(seq_i, image, image_mask, hi.norm_w, hi)
 
-        seq_a = self.forward_decoder(x_audio, x_fusion, audio_ids_restore, "audio", audio_ids_keep)
-        ha = self._dec["audio"][1]
-        loss_audio, pred_audio = Fn.PredLossFn.apply(seq_a, audio, audio_mask, ha.norm_w, ha)
+        with (torch.cuda.stream(side[0]) if side else contextlib.nullcontext()):
+            seq_a = self.forward_decoder(x_audio, x_fusion, audio_ids_restore, "audio", audio_ids_keep)
+            ha = self._dec["audio"][1]
+            loss_audio, pred_audio = Fn.PredLossFn.apply(seq_a, audio, audio_mask, ha.norm_w, ha)
+        if side:
+            cur.wait_stream(side[0])
         return loss_image, loss_audio, pred_image, pred_audio

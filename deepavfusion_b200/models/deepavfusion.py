@@ -12,6 +12,11 @@ from functools import partial
 import torch
 from torch import nn
 
+import contextlib
+import os
+from types import SimpleNamespace
+
+from .. import functional as Fn
 from . import fusion_blocks, vits
 from .layers import FinalNorm, ensure_store
 from .vits import _xavier_linear_
@@ -80,23 +85,67 @@ class DeepAVFusion(nn.Module):
         with ensure_store(self):
             return self._forward(image, audio, image_ids_keep, audio_ids_keep, return_embs)
 
+    def _bind(self, store):
+        self._tok_ns = SimpleNamespace(store=store, tokens=self.fusion_tokens)
+
+    def _side_streams(self, device):
+        """Two side streams: within a layer the image block, the audio block and the fusion block read the
+        same inputs and are independent, so they are issued on three streams.  Autograd runs
+        each node's backward on its forward stream, so backward overlaps the same way, and a CUDA-graph
+        capture of the step records the branches as parallel graph paths.  The many small fusion-block
+        kernels (grids of 8-72 CTAs) then fill SMs the modality blocks leave idle."""
+        if device.type != "cuda" or os.environ.get("DAVF_STREAMS", "1") == "0":
+            return None
+        st = self.__dict__.get("_davf_streams")
+        if st is None or st[0].device != device:
+            st = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self.__dict__["_davf_streams"] = st
+        store = self.__dict__.get("_davf_store")
+        if store is not None and st[0] not in store.side_streams:
+            store.side_streams.extend(st)
+        return st
+
     def _forward(self, image, audio, image_ids_keep, audio_ids_keep, return_embs):
         B = image.shape[0]
+        side = self._side_streams(image.device)
+        cur = torch.cuda.current_stream() if side else None
+
+        def on(stream):
+            return torch.cuda.stream(stream) if side else contextlib.nullcontext()
+
+        def fork():
+            if side:
+                side[0].wait_stream(cur)
+                side[1].wait_stream(cur)
+
+        def join():
+            if side:
+                cur.wait_stream(side[0])
+                cur.wait_stream(side[1])
+
+        fork()
         x_image = self.image.prepare_patch_tokens(image, image_ids_keep)      # (B, nI, D) f32
-        x_audio = self.audio.prepare_patch_tokens(audio, audio_ids_keep)      # (B, nA, D)
+        with on(side[0] if side else None):
+            x_audio = self.audio.prepare_patch_tokens(audio, audio_ids_keep)  # (B, nA, D)
+        join()
         embs = []
-        x_fusion = self.fusion_tokens.expand(B, -1, -1)
+        x_fusion = Fn.BroadcastTokensFn.apply(self.fusion_tokens, B, self._tok_ns)
         for blk_image, blk_audio, blk_fusion in zip(self.image.blocks, self.audio.blocks, self.fusion_blocks):
+            fork()
             if blk_fusion is None:
                 x_image = blk_image(x_image)
-                x_audio = blk_audio(x_audio)
+                with on(side[0] if side else None):
+                    x_audio = blk_audio(x_audio)
             else:
                 # deepavfusion.py:104-107: the modality blocks see the fusion tokens as extra keys / values;
                 # the fusion block reads the PRE-block modality tokens.
                 _x_image = blk_image(x_image, prefix=x_fusion)
-                _x_audio = blk_audio(x_audio, prefix=x_fusion)
-                x_fusion = blk_fusion(x_fusion, x_image, x_audio)
+                with on(side[0] if side else None):
+                    _x_audio = blk_audio(x_audio, prefix=x_fusion)
+                with on(side[1] if side else None):
+                    x_fusion = blk_fusion(x_fusion, x_image, x_audio)
                 x_image, x_audio = _x_image, _x_audio
+            join()
             if return_embs:
                 embs.append((x_image, x_audio, x_fusion))
         x_image = self.image.norm(x_image)

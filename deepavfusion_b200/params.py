@@ -95,6 +95,8 @@ class ParamStore:
         self._versions = None
         self._depth = 0
         self.sync = None          # optional util.distributed.GradSync (data-parallel bucket all-reduce)
+        self.side_streams = []    # streams the model issues independent branches on (see DeepAVFusion._side_streams)
+        self._join_pending = False
         self.refresh_lowp(force=True)
 
     # -- re-entrancy: nested module forwards skip the per-forward checks ------------------------
@@ -191,3 +193,21 @@ class ParamStore:
         are all enqueued.  Drives the overlapped bucket all-reduce when data-parallel."""
         if self.sync is not None:
             self.sync.params_done([self._index[id(p)] for p in params if p.requires_grad])
+        self._schedule_join()
+
+    def _schedule_join(self) -> None:
+        """Parameter gradients are written by our kernels directly into ``flat_g`` on whatever stream the
+        backward node runs on -- autograd does not know about them, so it does not order them before the
+        caller's stream at the end of ``backward()``.  Queue (once per backward pass) an engine callback that
+        makes the caller's stream wait for the side streams before anything (optimizer, all-reduce, grad
+        norm) reads the gradients."""
+        if not self.side_streams or self._join_pending:
+            return
+        self._join_pending = True
+
+        def join():
+            self._join_pending = False
+            cur = torch.cuda.current_stream()
+            for s in self.side_streams:
+                cur.wait_stream(s)
+        torch.autograd.Variable._execution_engine.queue_callback(join)

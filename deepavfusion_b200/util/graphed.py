@@ -9,7 +9,8 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, trainer, image_example: torch.Tensor, audio_example: torch.Tensor, warmup: int = 3):
+    def __init__(self, trainer, image_example: torch.Tensor, audio_example: torch.Tensor, warmup: int = 3,
+                 capture_error_mode: str = "thread_local"):
         assert trainer.accum_iter == 1, "graph capture covers one full optimizer step (accum_iter == 1)"
         self.trainer = trainer
         self.image = torch.empty_like(image_example)
@@ -29,7 +30,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         from .. import kernels as K
         n0 = K.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss_image, self.loss_audio, self.grad_norm = self._one_step(sync_hp=False)
         self.launches_per_step = K.launch_count() - n0
 
