@@ -37,7 +37,7 @@ constexpr int kStageCols = 16;                         // columns per epilogue c
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
 constexpr uint32_t kStagingBytes = kNumEpiWarps * 32 * kStagePitch * 4;
 constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
-constexpr uint64_t kSpinLimit = 4000000000ull;   // ~2 s of SM clocks: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 20000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -47,23 +47,37 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// try_wait suspends the thread for a bounded, implementation-defined time per call, so a spin COUNT bounds
+// the wall time: a broken pipeline traps after a few seconds instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {
       printf("davf gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -238,7 +252,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (so ptxas keeps the loop state and addresses in uniform registers);
+    // one elected lane issues the expect_tx + TMA instructions.
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -246,29 +263,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (dbg && t == 0 && kb == kb0) dbg[1] = clock64();
+          if (dbg && t == 0 && kb == kb0 && leader) dbg[1] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          if (A_KMAJOR) {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-          } else {
+          if (leader) {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            if (A_KMAJOR) {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
-          }
-          if (B_KMAJOR) {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+            }
+            if (B_KMAJOR) {
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Warp-uniform loop (barrier waits, descriptor arithmetic in uniform registers); one elected lane
+    // issues tcgen05.mma / tcgen05.commit.  With the loop inside `if (lane == 0)` every operand had to be
+    // moved vector->uniform register per instruction and the issue path, not the tensor pipe, set the pace.
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -285,24 +309,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (dbg && t == 0 && kb == kb0) dbg[2] = clock64();
+          if (dbg && t == 0 && kb == kb0 && leader) dbg[2] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
+          const uint64_t adesc0 = A_KMAJOR ? make_smem_desc(sa, 16, 1024) : make_smem_desc(sa, 8192, 1024);
+          const uint64_t bdesc0 = B_KMAJOR ? make_smem_desc(sb, 16, 1024) : make_smem_desc(sb, 8192, 1024);
+          constexpr uint32_t A_STEP = (A_KMAJOR ? UMMA_K * 2 : UMMA_K * 128) >> 4;   // descriptor address units of 16 B
+          constexpr uint32_t B_STEP = (B_KMAJOR ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = A_KMAJOR ? make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024)
-                                            : make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024);
-            const uint64_t bdesc = B_KMAJOR ? make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024)
-                                            : make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024);
-            umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
-              umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = adesc0 + (uint64_t)(k * A_STEP), bdesc = bdesc0 + (uint64_t)(k * B_STEP);
+              umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
+                umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
-        if (dbg && t == 0) dbg[3] = clock64();
+        if (leader) umma_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+        __syncwarp();
+        if (dbg && t == 0 && leader) dbg[3] = clock64();
       }
     }
   } else {
