@@ -83,6 +83,7 @@ SIGNATURES = {
     "davf_device_sm": (i, []),
     "davf_set_gemm_impl": (i, [i]),
     "davf_get_gemm_impl": (i, []),
+    "davf_set_gemm_2cta": (i, [i]),
     "davf_set_attn_impl": (i, [i]),
     "davf_launch_count": (i64, []),
     "davf_mask_rank": (i, [vp, i, i, i, vp, vp, vp, vp]),

@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
   load_tile<DQK>(Ks, a.k + (int64_t)b * a.k_bs + h * DQK, a.k_rs, Nk, Nkp);
   load_tile<DV>(Vs, a.v + (int64_t)b * a.v_bs + h * DV, a.v_rs, Nk, Nkp);
   load_tile<DV>(dOs, a.d_o + (int64_t)b * a.do_bs + h * DV, a.do_rs, Nq, Nqp);
-  for (int i = threadIdx.x; i < Nqp; i += blockDim.x) Ls[i] = i < Nq ? a.lse[((int64_t)b * a.H + h) * Nq + i] * kLog2e : 0.f;
+  for (int i = threadIdx.x; i < Nqp; i += blockDim.x) {
+    Ls[i] = i < Nq ? a.lse[((int64_t)b * a.H + h) * Nq + i] * kLog2e : 0.f;
+    Ds[i] = 0.f;     // padded queries are never written by phase A; 0 * (uninitialised NaN) would poison dK in phase B
+  }
   __syncthreads();
   const float sl = a.scale * kLog2e;
 

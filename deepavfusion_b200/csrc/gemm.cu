@@ -13,6 +13,8 @@ extern "C" int davf_set_gemm_impl(int impl) {
   return DAVF_OK;
 }
 extern "C" int davf_get_gemm_impl(void) { return g_gemm_impl.load(); }
+namespace davf { int gemm_set_2cta(int on); }
+extern "C" int davf_set_gemm_2cta(int on) { return davf::gemm_set_2cta(on); }
 
 extern "C" int davf_gemm(const davf_gemm_args* a, davf_stream_t s) {
   DAVF_CHECK_ARG(a && a->a && a->b && a->out, "gemm: null pointer");

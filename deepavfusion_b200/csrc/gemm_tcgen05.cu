@@ -23,6 +23,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <string.h>
+#include <stdlib.h>
 
 #include "gemm_epilogue.cuh"
 
@@ -37,7 +38,7 @@ constexpr int kStageCols = 16;                         // columns per epilogue c
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
 constexpr uint32_t kStagingBytes = kNumEpiWarps * 32 * kStagePitch * 4;
 constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
-constexpr uint32_t kSpinLimit = 20000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 4000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -91,6 +92,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA variants (CTA pair = cluster of 2): every TMA signals the mbarrier of the pair's leader CTA (peer bit
+// of the shared::cluster address cleared), the MMA spans both CTAs' shared / tensor memory.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta_rank) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -191,15 +229,23 @@ struct EpiSel {
   __device__ __forceinline__ static bool remap(const EpiParams& p) { return kStatic ? false : (p.g > 0 || p.res_idx != nullptr); }
 };
 
-template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI>
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN
+// tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of B (BN/2 rows), the
+// MMA reads both halves, so the shared-memory fill traffic per FLOP halves (the 1-CTA kernel is bound by the
+// per-SM TMA fill rate, not by the tensor pipe).  TileSched m-blocks are 128*CG rows.
+template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                TileSched ts, EpiParams ep) {
+  constexpr int BNL = BN / CG;                       // B rows staged by this CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = BNL * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool lead_cta = cta_rank == 0;
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   constexpr uint32_t TMEM_COLS = 512;               // two accumulator stages of BN columns (+ 2 x 16 row-sum columns when BN = 128)
-  constexpr uint32_t IDESC = make_idesc(BM, BN, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1);
+  constexpr uint32_t IDESC = make_idesc(BM * CG, BN, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1);
   constexpr uint32_t IDESC_ONES = make_idesc(BM, 16, A_KMAJOR ? 0 : 1, 0);
   constexpr uint32_t ROWSUM_COL = 2 * BN;           // only used when BN == 128 (host enforces it)
 
@@ -227,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps);
+      mbar_init(tempty_bar(a), kNumEpiWarps * CG);     // the leader's barrier collects the epilogue warps of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -237,17 +283,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrive / TMA
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
   const int num_tiles = ts.num_tiles();
-  long long* dbg = (ep.debug_clocks && blockIdx.x == 0) ? ep.debug_clocks : nullptr;   // optional timeline probe of CTA 0
+  long long* dbg = (CG == 1 && ep.debug_clocks && blockIdx.x == 0) ? ep.debug_clocks : nullptr;   // optional timeline probe of CTA 0
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0) {
@@ -258,27 +309,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      auto tma = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+        if (CG == 2) tma_load_2d_2cta(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int m_blk, n_blk, sp, kb0, kb1;
         ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+        const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM;      // this CTA's rows of A
+        const int n0 = n_blk * BN + (int)cta_rank * BNL;             // this CTA's rows of B
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (dbg && t == 0 && kb == kb0 && leader) dbg[1] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (leader) {
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            if (lead_cta) mbar_expect_tx(full_bar(stage), STAGE_BYTES * CG);   // bytes of both CTAs land on the leader's barrier
             if (A_KMAJOR) {
-              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+              tma(sa, &tmap_a, full_bar(stage), kb * BK, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmap_a, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma(sa + j * 8192, &tmap_a, full_bar(stage), m0 + j * 64, kb * BK);
             }
             if (B_KMAJOR) {
-              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+              tma(sb, &tmap_b, full_bar(stage), kb * BK, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BNL / 64; ++j) tma(sb + j * 8192, &tmap_b, full_bar(stage), n0 + j * 64, kb * BK);
             }
           }
           __syncwarp();
@@ -291,12 +347,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Warp-uniform loop (barrier waits, descriptor arithmetic in uniform registers); one elected lane
     // issues tcgen05.mma / tcgen05.commit.  With the loop inside `if (lane == 0)` every operand had to be
     // moved vector->uniform register per instruction and the issue path, not the tensor pipe, set the pace.
-    {
+    if (lead_cta) {                                  // the pair's MMAs are issued by the leader CTA only
       const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
         int m_blk, n_blk, sp, kb0, kb1;
         ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
         const int acc = local & 1;
@@ -320,16 +376,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = adesc0 + (uint64_t)(k * A_STEP), bdesc = bdesc0 + (uint64_t)(k * B_STEP);
-              umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-              if (rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
+              if (CG == 2) umma_f16_2cta(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CG == 1 && rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
                 umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs retire
+            if (CG == 2) umma_commit_2cta(empty_bar(stage)); else umma_commit(empty_bar(stage));   // frees the smem slot(s) once these MMAs retire
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (leader) umma_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+        if (leader) { if (CG == 2) umma_commit_2cta(tfull_bar(acc)); else umma_commit(tfull_bar(acc)); }   // accumulator complete -> epilogue(s)
         __syncwarp();
         if (dbg && t == 0 && leader) dbg[3] = clock64();
       }
@@ -350,12 +407,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
     struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
     int local = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
       int m_blk, n_blk, sp, kb0, kb1;
       ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1u;
-      const int64_t m_base = (int64_t)m_blk * BM + quad * 32;
+      const int64_t m_base = (int64_t)m_blk * (BM * CG) + cta_rank * BM + quad * 32;
       // per-tile row bookkeeping for the 4 rows this lane touches in the coalesced phase
       int64_t out_off[4], res_off[4], aux_off[4];
       bool rvalid[4];
@@ -390,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (dbg && t == 0 && warp == 2 && lane == 0) dbg[4] = clock64();
-      if (want_rowsum && n_blk == 0 && half == 0) {
+      if (CG == 1 && want_rowsum && n_blk == 0 && half == 0) {
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
@@ -404,7 +461,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (c == NCHUNK - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CG == 2 && !lead_cta) mbar_arrive_remote(tempty_bar(acc), 0);   // the leader CTA's MMA warp owns the hand-shake
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
 #pragma unroll
         for (int j = 0; j < kStageCols; j += 4)
@@ -459,11 +519,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncwarp();          // lanes 1..31 of the producer / MMA warps skipped the role loops: reconverge, so that the
                          // aligned barrier below is executed once per warp (a divergent bar.sync counts a warp twice)
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's smem / barriers / TMEM stay valid until both CTAs are done
   if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -539,20 +600,32 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
-template <int BN, int STAGES, bool AK, bool BKM, int EPI>
+template <int BN, int STAGES, bool AK, bool BKM, int EPI, int CG>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + kStagingBytes + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + kStagingBytes + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI>;
+  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG>;
   if (!attr_set) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int tiles = ts.m_tiles * ts.n_tiles * ts.splits;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, kNumThreads, smem, st>>>(ta, tb, ts, ep);
-  DAVF_LAUNCH_OK();
+  const int clusters = tiles < kNumSMs / CG ? tiles : kNumSMs / CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG > 1 ? 1 : 0;
+  DAVF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ts, ep));
+  g_launches.fetch_add(1);
   return DAVF_OK;
 }
 
@@ -570,61 +643,95 @@ static int epi_mask(const davf_gemm_args& a) {
   return m;
 }
 
-template <int BN, int STAGES>
+static bool has_static_epi(const davf_gemm_args& a) {
+  const int em = epi_mask(a);
+  if (a.a_kmajor && a.b_kmajor) return em == (EPI_BIAS | EPI_BF16) || em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16) || em == (EPI_BIAS | EPI_RES);
+  if (a.a_kmajor && !a.b_kmajor) return em == EPI_BF16 || em == (EPI_DGELU | EPI_BF16);
+  if (!a.a_kmajor && !a.b_kmajor) return em == EPI_RED;
+  return false;
+}
+
+template <int BN, int STAGES, int CG>
 static int launch_major(const davf_gemm_args& a, const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, cudaStream_t st) {
   const EpiParams ep = make_epi(a);
   const int em = epi_mask(a);
   if (a.a_kmajor && a.b_kmajor) {            // forward
-    if (em == (EPI_BIAS | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_BF16>(ta, tb, ts, ep, st);
-    if (em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16>(ta, tb, ts, ep, st);
-    if (em == (EPI_BIAS | EPI_RES)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_RES>(ta, tb, ts, ep, st);
-    return launch_cfg<BN, STAGES, true, true, -1>(ta, tb, ts, ep, st);
+    if (em == (EPI_BIAS | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_BF16, CG>(ta, tb, ts, ep, st);
+    if (em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16, CG>(ta, tb, ts, ep, st);
+    if (em == (EPI_BIAS | EPI_RES)) return launch_cfg<BN, STAGES, true, true, EPI_BIAS | EPI_RES, CG>(ta, tb, ts, ep, st);
+    if constexpr (CG == 1) return launch_cfg<BN, STAGES, true, true, -1, 1>(ta, tb, ts, ep, st);
+  } else if (a.a_kmajor && !a.b_kmajor) {    // dgrad
+    if (em == EPI_BF16) return launch_cfg<BN, STAGES, true, false, EPI_BF16, CG>(ta, tb, ts, ep, st);
+    if (em == (EPI_DGELU | EPI_BF16)) return launch_cfg<BN, STAGES, true, false, EPI_DGELU | EPI_BF16, CG>(ta, tb, ts, ep, st);
+    if constexpr (CG == 1) return launch_cfg<BN, STAGES, true, false, -1, 1>(ta, tb, ts, ep, st);
+  } else if (!a.a_kmajor && !a.b_kmajor) {   // wgrad (row-sum launches take the generic 1-CTA kernel)
+    if (em == EPI_RED) return launch_cfg<BN, STAGES, false, false, EPI_RED, CG>(ta, tb, ts, ep, st);
+    if constexpr (CG == 1) return launch_cfg<BN, STAGES, false, false, -1, 1>(ta, tb, ts, ep, st);
+  } else {
+    if constexpr (CG == 1) return launch_cfg<BN, STAGES, false, true, -1, 1>(ta, tb, ts, ep, st);
   }
-  if (a.a_kmajor && !a.b_kmajor) {           // dgrad
-    if (em == EPI_BF16) return launch_cfg<BN, STAGES, true, false, EPI_BF16>(ta, tb, ts, ep, st);
-    if (em == (EPI_DGELU | EPI_BF16)) return launch_cfg<BN, STAGES, true, false, EPI_DGELU | EPI_BF16>(ta, tb, ts, ep, st);
-    return launch_cfg<BN, STAGES, true, false, -1>(ta, tb, ts, ep, st);
-  }
-  if (!a.a_kmajor && !a.b_kmajor) {          // wgrad (row-sum launches take the generic kernel)
-    if (em == EPI_RED) return launch_cfg<BN, STAGES, false, false, EPI_RED>(ta, tb, ts, ep, st);
-    return launch_cfg<BN, STAGES, false, false, -1>(ta, tb, ts, ep, st);
-  }
-  return launch_cfg<BN, STAGES, false, true, -1>(ta, tb, ts, ep, st);
+  set_error("gemm: no kernel for this configuration");
+  return DAVF_EUNSUPPORTED;
 }
 
+static std::atomic<int> g_allow_2cta{1};
+
 int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
+  const int kb_total = (int)((a.K + BK - 1) / BK);
+  auto pick_splits = [&](int64_t mn_tiles, int units) {
+    int splits = a.split_k;
+    if (splits <= 0) {   // auto: fill the machine when the caller allows atomic accumulation
+      splits = 1;
+      if (a.accumulate) {
+        if (mn_tiles < units) splits = (int)((units + mn_tiles - 1) / mn_tiles);
+        if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+      }
+    }
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    const int per = (kb_total + splits - 1) / splits;
+    return std::make_pair((kb_total + per - 1) / per, per);      // no empty split
+  };
+  CUtensorMap ta, tb;
+  int rc;
+  // ---- CTA-pair path: 256 x 256 tiles, tcgen05.mma.cta_group::2 -----------------------------------
+  static const int class_mask = [] { const char* e = getenv("DAVF_2CTA_CLASSES"); return e ? atoi(e) : 7; }();   // debug: 1 fwd, 2 dgrad, 4 wgrad
+  const int cls = (a.a_kmajor && a.b_kmajor) ? 1 : (a.a_kmajor ? 2 : 4);
+  if (g_allow_2cta.load() && (class_mask & cls) && has_static_epi(a) && a.M >= 256 && a.N >= 256) {
+    const int64_t m2 = (a.M + 2 * BM - 1) / (2 * BM), n2 = (a.N + 255) / 256;
+    const auto sp = pick_splits(m2 * n2, kNumSMs / 2);
+    // worth it when the pair tiles fill at least ~half of the 74 SM pairs; otherwise 128-wide 1-CTA tiles
+    // give more parallelism
+    if (m2 * n2 * sp.first >= 36) {
+      TileSched ts{(int)m2, (int)n2, sp.first, kb_total, sp.second};
+      if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
+      else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
+      if (rc) return rc;
+      if (a.b_kmajor) rc = get_tensor_map(a.b, a.K, a.N, a.ldb, 128, &tb);
+      else rc = get_tensor_map(a.b, a.N, a.K, a.ldb, BK, &tb);
+      if (rc) return rc;
+      return launch_major<256, 6, 2>(a, ta, tb, ts, st);
+    }
+  }
+  // ---- single-CTA path --------------------------------------------------------------------------------
   // tile-N choice: 256-wide tiles halve the shared-memory operand traffic per FLOP; use them when
   // the problem still yields at least ~one full wave of CTAs, otherwise 128 for parallelism.
   const int64_t m_tiles = (a.M + BM - 1) / BM;
   int bn = 128;
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs && !a.rowsum_out) bn = 256;   // row-sum columns need BN = 128
   const int64_t n_tiles = (a.N + bn - 1) / bn;
-  const int kb_total = (int)((a.K + BK - 1) / BK);
-  int splits = a.split_k;
-  if (splits <= 0) {   // auto: fill the machine when the caller allows atomic accumulation
-    splits = 1;
-    if (a.accumulate) {
-      const int64_t mn = m_tiles * n_tiles;
-      if (mn < kNumSMs) splits = (int)((kNumSMs + mn - 1) / mn);
-      if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
-    }
-  }
-  if (splits > kb_total) splits = kb_total;
-  if (splits < 1) splits = 1;
-  int per = (kb_total + splits - 1) / splits;
-  splits = (kb_total + per - 1) / per;          // no empty split
-  TileSched ts{(int)m_tiles, (int)n_tiles, splits, kb_total, per};
-
-  CUtensorMap ta, tb;
-  int rc;
+  const auto sp = pick_splits(m_tiles * n_tiles, kNumSMs);
+  TileSched ts{(int)m_tiles, (int)n_tiles, sp.first, kb_total, sp.second};
   if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
   else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
   if (rc) return rc;
   if (a.b_kmajor) rc = get_tensor_map(a.b, a.K, a.N, a.ldb, bn, &tb);
   else rc = get_tensor_map(a.b, a.N, a.K, a.ldb, BK, &tb);
   if (rc) return rc;
-  if (bn == 256) return launch_major<256, 4>(a, ta, tb, ts, st);
-  return launch_major<128, 6>(a, ta, tb, ts, st);
+  if (bn == 256) return launch_major<256, 4, 1>(a, ta, tb, ts, st);
+  return launch_major<128, 6, 1>(a, ta, tb, ts, st);
 }
+
+int gemm_set_2cta(int on) { g_allow_2cta.store(on ? 1 : 0); return 0; }
 
 }  // namespace davf

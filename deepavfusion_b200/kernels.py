@@ -386,5 +386,9 @@ def set_gemm_impl(impl: int) -> None:
     check(_cabi.lib().davf_set_gemm_impl(impl), "davf_set_gemm_impl")
 
 
+def set_gemm_2cta(on: bool) -> None:
+    check(_cabi.lib().davf_set_gemm_2cta(int(on)), "davf_set_gemm_2cta")
+
+
 def set_attn_impl(impl: int) -> None:
     check(_cabi.lib().davf_set_attn_impl(impl), "davf_set_attn_impl")

@@ -137,6 +137,8 @@ class AVMAE(nn.Module):
         cur = torch.cuda.current_stream() if side else None
         if side:
             side[0].wait_stream(cur)
+            for t in (x_audio, x_fusion, audio, audio_mask, audio_ids_restore, audio_ids_keep):
+                t.record_stream(side[0])              # allocated on `cur`, read by the audio decoder's stream
         seq_i = self.forward_decoder(x_image, x_fusion, image_ids_restore, "image", image_ids_keep)
         hi = self._dec["image"][1]
         loss_image, pred_image = Fn.PredLossFn.apply(seq_i, image, image_mask, hi.norm_w, hi)
@@ -147,4 +149,6 @@ class AVMAE(nn.Module):
             loss_audio, pred_audio = Fn.PredLossFn.apply(seq_a, audio, audio_mask, ha.norm_w, ha)
         if side:
             cur.wait_stream(side[0])
+            loss_audio.record_stream(cur)
+            pred_audio.record_stream(cur)
         return loss_image, loss_audio, pred_image, pred_audio

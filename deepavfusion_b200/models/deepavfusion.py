@@ -101,8 +101,10 @@ class DeepAVFusion(nn.Module):
             st = (torch.cuda.Stream(device), torch.cuda.Stream(device))
             self.__dict__["_davf_streams"] = st
         store = self.__dict__.get("_davf_store")
-        if store is not None and st[0] not in store.side_streams:
-            store.side_streams.extend(st)
+        if store is not None:
+            if st[0] not in store.side_streams:
+                store.side_streams.extend(st)
+            store.main_stream = torch.cuda.current_stream()
         return st
 
     def _forward(self, image, audio, image_ids_keep, audio_ids_keep, return_embs):
@@ -123,6 +125,15 @@ class DeepAVFusion(nn.Module):
                 cur.wait_stream(side[0])
                 cur.wait_stream(side[1])
 
+        def share(t, *streams):
+            """``t`` is read by kernels on ``streams`` other than the one it was allocated on: tell the caching
+            allocator, or its block could be re-used (by the allocating stream) while those kernels still run
+            -- in particular when autograd frees saved activations during the multi-stream backward."""
+            if side:
+                for s in streams:
+                    t.record_stream(s)
+            return t
+
         fork()
         x_image = self.image.prepare_patch_tokens(image, image_ids_keep)      # (B, nI, D) f32
         with on(side[0] if side else None):
@@ -130,6 +141,8 @@ class DeepAVFusion(nn.Module):
         join()
         embs = []
         x_fusion = Fn.BroadcastTokensFn.apply(self.fusion_tokens, B, self._tok_ns)
+        if side:
+            share(x_image, side[1]); share(x_audio, cur, side[1]); share(x_fusion, side[0], side[1])
         for blk_image, blk_audio, blk_fusion in zip(self.image.blocks, self.audio.blocks, self.fusion_blocks):
             fork()
             if blk_fusion is None:
@@ -146,6 +159,8 @@ class DeepAVFusion(nn.Module):
                     x_fusion = blk_fusion(x_fusion, x_image, x_audio)
                 x_image, x_audio = _x_image, _x_audio
             join()
+            if side:      # next layer (and the final norms on `cur`) read these across streams
+                share(x_image, side[1]); share(x_audio, cur, side[1]); share(x_fusion, cur, side[0])
             if return_embs:
                 embs.append((x_image, x_audio, x_fusion))
         x_image = self.image.norm(x_image)

@@ -96,6 +96,7 @@ class ParamStore:
         self._depth = 0
         self.sync = None          # optional util.distributed.GradSync (data-parallel bucket all-reduce)
         self.side_streams = []    # streams the model issues independent branches on (see DeepAVFusion._side_streams)
+        self.main_stream = None   # the stream the current forward was issued on
         self._join_pending = False
         self.refresh_lowp(force=True)
 
@@ -207,7 +208,16 @@ class ParamStore:
 
         def join():
             self._join_pending = False
-            cur = torch.cuda.current_stream()
-            for s in self.side_streams:
-                cur.wait_stream(s)
+            self.join_side_streams(self.main_stream)
         torch.autograd.Variable._execution_engine.queue_callback(join)
+
+    def join_side_streams(self, stream=None) -> None:
+        """Make ``stream`` (default: the stream the last forward was issued on) wait for the side streams.
+        The engine callback may run on an autograd worker thread whose *current* stream is not the caller's,
+        so the caller's stream is remembered at forward time rather than queried here."""
+        if not self.side_streams:
+            return
+        cur = stream if stream is not None else (self.main_stream or torch.cuda.current_stream())
+        for s in self.side_streams:
+            if s != cur:
+                cur.wait_stream(s)

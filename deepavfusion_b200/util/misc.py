@@ -78,6 +78,7 @@ class Trainer:
         if self.sync is not None:
             self.sync.enabled = self.accums == self.accum_iter - 1       # all-reduce on the last micro-step only
         loss.backward()
+        self.store.join_side_streams(torch.cuda.current_stream() if self.store.flat_g.is_cuda else None)
         if self.sync is not None:
             self.sync.finish()
         self.accums += 1

@@ -41,6 +41,9 @@ int davf_device_sm(void);                     /* 100 for B200, <0 on error      
 /* 0 = tcgen05/TMA GEMM (default), 1 = SIMT checker GEMM (debug only; set by tests) */
 int davf_set_gemm_impl(int impl);
 int davf_get_gemm_impl(void);
+/* 1 (default): large launches use the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles);
+ * 0: single-CTA kernel only (A/B comparison in tests and benches). */
+int davf_set_gemm_2cta(int on);
 /* 0 = tensor-core attention (default), 1 = CUDA-core checker attention (debug only; set by tests) */
 int davf_set_attn_impl(int impl);
 /* Number of kernel launches issued by this library since process start (bench gpu_launches). */

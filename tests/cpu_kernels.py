@@ -282,6 +282,10 @@ def set_attn_impl(impl):
     pass
 
 
+def set_gemm_2cta(on):
+    pass
+
+
 def install(monkeypatch=None):
     """Replace every kernel wrapper in deepavfusion_b200.kernels by its emulation."""
     import deepavfusion_b200.kernels as K

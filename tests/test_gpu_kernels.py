@@ -175,6 +175,29 @@ gk = torch.zeros(192, 2 * D_, device='cuda')
 dyk = rnd(B_ * 8, 192, seed=13, dtype=bf16)
 K.gemm(dyk, tok, False, False, out=gk[:, D_:], accumulate=True)
 check('col-slice wgrad', gk[:, D_:], dyk.float().t() @ tok.float()); assert float(gk[:, :D_].abs().max()) == 0
+# ---- statically specialised epilogues; large enough for the CTA-pair (cta_group::2) kernel, incl. ragged M
+for two in ([1, 0] if impl == 0 else [0]):
+    K.set_gemm_2cta(bool(two))
+    tag = '2cta' if two else '1cta'
+    for (M, N, Kd) in [(3136, 2304, 768), (14592, 2048, 512), (3000, 768, 1536), (5184, 768, 2304), (257, 4096, 320)]:
+        a, b, bias = rnd(M, Kd, seed=21, dtype=bf16), rnd(N, Kd, seed=22, dtype=bf16) * 0.05, rnd(N, seed=23)
+        ac, bc, biasc = a.cpu(), b.cpu(), bias.cpu()
+        check(f'{{tag}} bias bf16 {{M}}x{{N}}x{{Kd}}', K.gemm(a, b, bias=bias), E.gemm(ac, bc, bias=biasc))
+        g_, h_ = K.gemm(a, b, bias=bias, act=K.ACT_GELU, want_aux=True)
+        eg_, eh_ = E.gemm(ac, bc, bias=biasc, act=E.ACT_GELU, want_aux=True)
+        check(f'{{tag}} gelu out {{M}}x{{N}}x{{Kd}}', g_, eg_); check(f'{{tag}} gelu aux', h_, eh_)
+        res = rnd(M, N, seed=24)
+        check(f'{{tag}} bias+res f32 {{M}}x{{N}}x{{Kd}}', K.gemm(a, b, bias=bias, res=res, out_dtype=torch.float32),
+              E.gemm(ac, bc, bias=biasc, res=res.cpu(), out_dtype=torch.float32))
+        dy = rnd(M, N, seed=25, dtype=bf16)                       # dgrad: [M,N] x W[N,Kd] (MN-major B)
+        check(f'{{tag}} dgrad bf16 {{M}}x{{Kd}}x{{N}}', K.gemm(dy, b, True, False), E.gemm(dy.cpu(), bc, True, False))
+        hpre = rnd(M, Kd, seed=26, dtype=bf16)
+        check(f'{{tag}} dgelu {{M}}x{{Kd}}x{{N}}', K.gemm(dy, b, True, False, act=K.ACT_DGELU, aux_in=hpre),
+              E.gemm(dy.cpu(), bc, True, False, act=E.ACT_DGELU, aux_in=hpre.cpu()))
+        gw = torch.ones(N, Kd, device='cuda')                     # wgrad without bias row-sum: static RED epilogue
+        K.gemm(dy, a, False, False, out=gw, accumulate=True)
+        check(f'{{tag}} wgrad red {{N}}x{{Kd}}x{{M}}', gw, 1 + dy.float().t() @ a.float(), 1e-2, 1e-1 * (M / 768) ** 0.5)
+K.set_gemm_2cta(True)
 torch.cuda.synchronize()
 print('FAILS', fails)
 sys.exit(1 if fails else 0)
