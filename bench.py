@@ -227,7 +227,7 @@ def run_ours(args):
     h_image, h_audio = synth_inputs(BATCH_PER_GPU, 1000 + rank, pinned=True)
     d_image, d_audio = h_image.to(dev), h_audio.to(dev)
     torch.manual_seed(2000 + rank)
-    use_graph = not args.no_graph and world == 1 or (args.graph_dp and not args.no_graph)
+    use_graph = not args.no_graph
 
     def eager_step(image, audio):
         li, la, _, _ = trainer.model(image, audio)
@@ -330,8 +330,10 @@ def run_ours(args):
                     vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=WORKLOAD, global_batch=BATCH_PER_GPU * world, parallelism=f"dp{world}",
                                 step="mask + fwd + bwd + grad all-reduce + fused AdamW", cuda_graph=bool(use_graph),
+                                streams=os.environ.get("DAVF_STREAMS", "1") != "0",
+                                allreduce=("none" if world == 1 else ("one NCCL call after the captured fwd+bwd graph" if use_graph else "bucketed, overlapped with backward")),
                                 l2="per-step working set (640 MB bf16 weights + >4 GB activations) exceeds the 126 MB L2; no flush needed",
-                                gflop_per_pair=GFLOP_PER_PAIR, step_tflops=step_tflops, step_frac_of_peak=step_tflops / peaks["tflops"]),
+                                gflop_per_pair=GFLOP_PER_PAIR, step_tflops=step_tflops, step_frac_of_peak=step_tflops / (peaks["tflops"] * world)),
                     e2e=dict(value=e2e_value, unit="clip-pairs/s", h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=4 * world,
                              ms_per_step=e2e_ms),
                     gpu_launches=int(launches_per_step * args.steps), launches_per_step=int(launches_per_step),
@@ -351,7 +353,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
-    ap.add_argument("--graph-dp", action="store_true", help="also capture the step (incl. NCCL) in a CUDA graph when N > 1")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-step", action="store_true", help="run one eager step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

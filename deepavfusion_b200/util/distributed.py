@@ -114,7 +114,13 @@ class GradSync:
         lo, hi = self.ranges[bi]
         buf = self.store.flat_g[lo:hi]
         if self.cuda:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            # the bucket's gradients were produced on several streams (image / audio / fusion branches run on
+            # their own streams): wait for everything enqueued so far on each of them
+            waits = [torch.cuda.current_stream()] + list(self.store.side_streams)
+            if self.store.main_stream is not None:
+                waits.append(self.store.main_stream)
+            for s in waits:
+                self.comm_stream.wait_stream(s)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         else:

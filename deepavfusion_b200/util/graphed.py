@@ -2,7 +2,12 @@
 replayed, removing the ~2,000 per-step launches' CPU cost and every host sync from the loop
 (eager PyTorch on this path is launch-bound).  Hyper-parameters (lr / weight decay,
 beta^t, grad scale) live in device tables the captured kernels read, so LR schedules need no
-re-capture; the mask noise comes from torch's graph-safe Philox generator state."""
+re-capture; the mask noise comes from torch's graph-safe Philox generator state.
+
+Data-parallel runs capture forward + backward only; the gradient all-reduce (one NCCL call over the flat
+f32 gradient buffer) and the fused AdamW launch follow the replay on the same stream.  (Capturing the
+bucketed, backward-overlapped NCCL calls inside the graph hung on this software stack; the eager
+``Trainer`` path keeps the overlap.)"""
 from __future__ import annotations
 
 import torch
@@ -28,19 +33,34 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         opt._sync_hp()
         self.graph = torch.cuda.CUDAGraph()
+        self.distributed = trainer.sync is not None
         from .. import kernels as K
         n0 = K.launch_count()
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
-            self.loss_image, self.loss_audio, self.grad_norm = self._one_step(sync_hp=False)
-        self.launches_per_step = K.launch_count() - n0
+            self.loss_image, self.loss_audio, self.grad_norm = self._one_step(sync_hp=False, capturing=True)
+        self.launches_per_step = K.launch_count() - n0 + (1 if self.distributed else 0)
 
-    def _one_step(self, sync_hp: bool = True):
+    def _one_step(self, sync_hp: bool = True, capturing: bool = False):
         tr = self.trainer
         li, la, _, _ = tr.model(self.image, self.audio)
+        if self.__dict__.get("distributed", tr.sync is not None):
+            tr.sync.enabled = False                      # no NCCL inside the captured region
+            (li + la).backward()
+            tr.store.join_side_streams(torch.cuda.current_stream())
+            if not capturing:
+                self._reduce_and_step(sync_hp)
+            return li.detach(), la.detach(), tr.optimizer.grad_norm()
         tr.backward(li + la)
         tr.optimizer.step(zero_grad=True, sync_hp=sync_hp)
         tr.accums = 0
         return li.detach(), la.detach(), tr.optimizer.grad_norm()
+
+    def _reduce_and_step(self, sync_hp: bool = True):
+        import torch.distributed as dist
+        tr = self.trainer
+        dist.all_reduce(tr.store.flat_g, op=dist.ReduceOp.SUM)      # 1/world is folded into AdamW's grad scale
+        tr.optimizer.step(zero_grad=True, sync_hp=sync_hp)
+        tr.accums = 0
 
     def __call__(self, image: torch.Tensor, audio: torch.Tensor):
         """image / audio may live on the host (pinned): the copies run on the current stream before the replay."""
@@ -48,6 +68,10 @@ class GraphedTrainStep:
         self.audio.copy_(audio, non_blocking=True)
         self.trainer.optimizer._sync_hp()
         self.graph.replay()
-        self.trainer.optimizer.n_steps += 1
+        if self.distributed:
+            self._reduce_and_step(sync_hp=False)
+            self.grad_norm = self.trainer.optimizer.grad_norm()
+        else:
+            self.trainer.optimizer.n_steps += 1
         self.trainer.n_steps += 1
         return self.loss_image, self.loss_audio, self.grad_norm
