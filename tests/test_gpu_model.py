@@ -97,3 +97,34 @@ def test_cpu_tensor_fails_loudly():
     image, audio = U.make_inputs(cfg, 1)
     with pytest.raises(RuntimeError):
         model(image, audio)
+
+
+def test_multistream_backward_matches_single_stream(monkeypatch):
+    """The three per-layer branches run on three streams (and the two decoders on two).  Gradients must be
+    identical in value to the single-stream run, iteration after iteration -- this is the regression test for
+    the uninitialised-shared-memory read (0 * NaN) that only concurrency exposed."""
+    cfg = O.OracleConfig(fusion_attn_ratio=0.25, fusion_mlp_ratio=1.0)
+    model = U.build_model(cfg, "cuda")
+    image, audio = U.make_inputs(cfg, 8)
+    image, audio = image.cuda(), audio.cuda()
+
+    def run():
+        model._davf_store.zero_grad()
+        torch.manual_seed(7)
+        li, la, _, _ = model(image, audio)
+        (li + la).backward()
+        model._davf_store.join_side_streams(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        return model._davf_store.flat_g.clone()
+
+    monkeypatch.setenv("DAVF_STREAMS", "0")
+    with torch.no_grad():
+        model(image, audio)                       # builds the store
+    ref = run()
+    assert bool(torch.isfinite(ref).all())
+    monkeypatch.setenv("DAVF_STREAMS", "1")
+    for it in range(12):
+        g = run()
+        assert bool(torch.isfinite(g).all()), f"non-finite gradient in multi-stream iteration {it}"
+        rel = ((g - ref).norm() / ref.norm()).item()
+        assert rel < 1e-3, (it, rel)
