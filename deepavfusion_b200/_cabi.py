@@ -71,7 +71,8 @@ class AttnBwdArgs(C.Structure):
                 ("dk", vp), ("dk_bs", C.c_int64), ("dk_rs", C.c_int64),
                 ("dv_", vp), ("dv_bs", C.c_int64), ("dv_rs", C.c_int64),
                 ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dqk", C.c_int), ("dv", C.c_int),
-                ("scale", C.c_float), ("accumulate_dq", C.c_int)]
+                ("scale", C.c_float), ("accumulate_dq", C.c_int),
+                ("o", vp), ("o_bs", C.c_int64), ("o_rs", C.c_int64)]
 
 
 i, i64, f = C.c_int, C.c_int64, C.c_float

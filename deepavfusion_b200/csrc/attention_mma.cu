@@ -223,6 +223,26 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
   }
   __syncthreads();
   const float sl = a.scale * kLog2e;
+  const bool have_o = a.o != nullptr;
+  if (have_o) {      // one-pass form: D_i = dO_i . O_i  (one thread per query row, 16-byte loads, all rows in flight)
+    for (int i = threadIdx.x; i < Nq; i += blockDim.x) {
+      const uint16_t* orow = a.o + (int64_t)b * a.o_bs + (int64_t)i * a.o_rs + h * DV;
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < DV; d += 8) {
+        const uint4 xo = *reinterpret_cast<const uint4*>(orow + d);
+        const uint4 yo = *reinterpret_cast<const uint4*>(dOs + i * (DV + 8) + d);
+        const uint32_t xs[4] = {xo.x, xo.y, xo.z, xo.w}, ys[4] = {yo.x, yo.y, yo.z, yo.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = unpack_bf16x2(xs[e]), y = unpack_bf16x2(ys[e]);
+          acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+        }
+      }
+      Ds[i] = acc;
+    }
+    __syncthreads();
+  }
 
   // ---------------- phase A ----------------
   for (int qt = warp; qt * 16 < Nq; qt += 8) {
@@ -231,8 +251,8 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
     load_a_frags<DV>(ado, dOs, qt * 16, lane);
     const int r0 = qt * 16 + g, r1 = r0 + 8;
     const float L0 = Ls[r0], L1 = Ls[r1];
-    float D0 = 0.f, D1 = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
+    float D0 = have_o ? Ds[r0] : 0.f, D1 = have_o ? Ds[r1] : 0.f;
+    for (int pass = have_o ? 1 : 0; pass < 2; ++pass) {
       float dq[DQK / 8][4];
 #pragma unroll
       for (int i = 0; i < DQK / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;

@@ -78,12 +78,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(davf_ln_fwd_args a, RowMap 
 
 template <int VEC>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap rm, int64_t rows) {
-  extern __shared__ float sm_red[];   // [2*D] : dgamma | dbeta partials of this CTA
+  extern __shared__ __align__(16) float sm_red[];   // [warps][2*D] : per-warp dgamma | dbeta partials
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)a.D;
-  for (int i = threadIdx.x; i < 2 * a.D; i += blockDim.x) sm_red[i] = 0.f;
-  __syncthreads();
   float4 gam[VEC], dg[VEC], db[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -144,19 +142,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap 
       }
     }
   }
-  // CTA-level reduction of dgamma / dbeta in shared memory, then one global atomic per column
+  // CTA-level reduction of dgamma / dbeta: every warp stores its partials (plain stores, no shared atomics),
+  // 4 columns per thread are summed over the warps, then ONE vector f32 reduction per 4 columns goes to HBM.
+  const int warp = threadIdx.x >> 5;
+  float* my = sm_red + (size_t)warp * 2 * a.D;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int col = (i * 32 + lane) * 4;
-    atomicAdd(&sm_red[col + 0], dg[i].x); atomicAdd(&sm_red[col + 1], dg[i].y);
-    atomicAdd(&sm_red[col + 2], dg[i].z); atomicAdd(&sm_red[col + 3], dg[i].w);
-    atomicAdd(&sm_red[a.D + col + 0], db[i].x); atomicAdd(&sm_red[a.D + col + 1], db[i].y);
-    atomicAdd(&sm_red[a.D + col + 2], db[i].z); atomicAdd(&sm_red[a.D + col + 3], db[i].w);
+    *reinterpret_cast<float4*>(my + col) = dg[i];
+    *reinterpret_cast<float4*>(my + a.D + col) = db[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.D; i += blockDim.x) {
-    if (a.dgamma) atomicAdd(a.dgamma + i, sm_red[i]);
-    if (a.dbeta) atomicAdd(a.dbeta + i, sm_red[a.D + i]);
+  for (int c4 = threadIdx.x; c4 < 2 * a.D / 4; c4 += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < wpb; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(sm_red + (size_t)w * 2 * a.D + c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* dst = c4 * 4 < a.D ? (a.dgamma ? a.dgamma + c4 * 4 : nullptr) : (a.dbeta ? a.dbeta + (c4 * 4 - a.D) : nullptr);
+    if (dst) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
   }
 }
 
@@ -213,10 +217,18 @@ extern "C" int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s) {
   const int64_t rows = (int64_t)a->B * rm.n;
   if (rows == 0) return DAVF_OK;
   const int wpb = 8;
-  int64_t blocks = (rows + wpb - 1) / wpb;
-  if (blocks > kNumSMs) blocks = kNumSMs;
-  const size_t smem = 2 * a->D * sizeof(float);
+  int64_t blocks = (rows + 2 * wpb - 1) / (2 * wpb);          // >= 2 rows per warp so the reduction tail amortises
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)wpb * 2 * a->D * sizeof(float);      // 48 KB at D = 768
   cudaStream_t st = as_stream(s);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set = true;
+  }
   switch (a->D / 128) {
     case 4: ln_bwd_kernel<4><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
     case 6: ln_bwd_kernel<6><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;

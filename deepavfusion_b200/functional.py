@@ -179,7 +179,7 @@ class AttnBranchFn(torch.autograd.Function):
             d5[:, :nP, 0].zero_()                                                     # dead queries
         q5 = qkv.view(B, S, 3, H, hd)
         K.attention_bwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], do.view(B, n, H, hd), lse, hd ** -0.5,
-                        d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2])
+                        d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2], o=o)
         dxn = linear_bwd(st, dqkv, xn, m.qkv_w, m.qkv_b)                              # [B*S, D] bf16
         gw, gb = st.grad(m.norm_w), st.grad(m.norm_b)
         if nP:

@@ -283,8 +283,9 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float, out: Optional[T
 
 
 def attention_bwd(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, lse: Tensor, scale: float,
-                  dq: Tensor, dk: Tensor, dv: Tensor, accumulate_dq: bool = False) -> None:
-    """Writes dq / dk / dv (strided bf16 views shaped like q / k / v)."""
+                  dq: Tensor, dk: Tensor, dv: Tensor, accumulate_dq: bool = False, o: Optional[Tensor] = None) -> None:
+    """Writes dq / dk / dv (strided bf16 views shaped like q / k / v).  ``o`` (forward output) is optional:
+    with it the kernel uses the one-pass D_i = dO_i . O_i form."""
     B, Nq, H, dqk = q.shape
     Nk, dvd = k.shape[1], v.shape[3]
     a = _cabi.AttnBwdArgs()
@@ -298,6 +299,9 @@ def attention_bwd(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, lse: Tensor, sca
     a.dv_, a.dv_bs, a.dv_rs = _bhs(dv, "dv")
     a.B, a.H, a.Nq, a.Nk, a.dqk, a.dv = B, H, Nq, Nk, dqk, dvd
     a.scale, a.accumulate_dq = float(scale), int(accumulate_dq)
+    if o is not None:
+        a.o, a.o_bs, a.o_rs = _bhs(o, "o")
+        assert a.o % 16 == 0 and a.o_bs % 8 == 0 and a.o_rs % 8 == 0, "o rows must be 16-byte aligned"
     check(_cabi.lib().davf_attention_bwd(C.byref(a), _stream()), "davf_attention_bwd")
 
 

@@ -178,9 +178,8 @@ int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s);
 
 /* Backward: given dO (layout of o) writes dq / dk / dv with the layouts of q / k / v (separate
  * stride sets so gradients can land in a packed dqkv buffer).  accumulate_dq != 0: dq += .
- * The softmax-Jacobian row term is computed as D_i = sum_j P_ij dP_ij from the recomputed
- * probabilities (not as dO_i . O_i from the bf16-rounded output), so the forward output is not
- * an input of the backward. */
+ * The softmax-Jacobian row term D_i is computed from the recomputed probabilities (exact, used for the
+ * tiny fusion-token attentions) unless the forward output `o` is supplied (see the struct). */
 typedef struct {
   const davf_bf16* q; int64_t q_bs; int64_t q_rs;
   const davf_bf16* k; int64_t k_bs; int64_t k_rs;
@@ -192,6 +191,9 @@ typedef struct {
   davf_bf16* dv_; int64_t dv_bs; int64_t dv_rs;
   int B; int H; int Nq; int Nk; int dqk; int dv;
   float scale; int accumulate_dq;
+  /* optional forward output (layout o_bs / o_rs, heads packed): if given, D_i = dO_i . O_i (one pass, the
+   * flash-attention form); if NULL, D_i = sum_j P_ij dP_ij from a first pass over the recomputed scores. */
+  const davf_bf16* o; int64_t o_bs; int64_t o_rs;
 } davf_attn_bwd_args;
 int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s);
 

@@ -184,12 +184,12 @@ def attention_fwd(q, k, v, scale, out=None, accumulate=False):
     return out, lse.contiguous()
 
 
-def attention_bwd(q, k, v, d_o, lse, scale, dq, dk, dv, accumulate_dq=False):
+def attention_bwd(q, k, v, d_o, lse, scale, dq, dk, dv, accumulate_dq=False, o=None):
     qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3)
     dof = d_o.float().permute(0, 2, 1, 3)
     p = torch.exp(qf @ kf.transpose(-1, -2) * scale - lse[..., None])
     dp = dof @ vf.transpose(-1, -2)
-    Dl = (p * dp).sum(-1, keepdim=True)
+    Dl = (p * dp).sum(-1, keepdim=True) if o is None else (dof * o.float().permute(0, 2, 1, 3)).sum(-1, keepdim=True)
     ds = p * (dp - Dl) * scale
     dqv = (ds @ kf).permute(0, 2, 1, 3)
     if accumulate_dq:

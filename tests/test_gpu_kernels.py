@@ -246,6 +246,11 @@ def _attention_case(K, B, H, Nq, Nk, dqk, dv, skip):
     close(dq, edq, 3e-2, 3e-2, "dq"); close(dk, edk, 3e-2, 3e-2, "dk"); close(dvv, edv, 3e-2, 3e-2, "dv")
     K.attention_bwd(q, k, v, do, lse, scale, dq, dk, dvv, accumulate_dq=True)
     close(dq, 2 * edq.float(), 4e-2, 4e-2, "dq accumulate")
+    # one-pass form with the forward output supplied (used by the encoder / decoder blocks)
+    dq2, dk2, dv2 = torch.zeros_like(dq), torch.zeros_like(dk), torch.zeros_like(dvv)
+    K.attention_bwd(q, k, v, do, lse, scale, dq2, dk2, dv2, o=o)
+    E.attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), lse.cpu(), scale, edq, edk, edv, o=o.cpu())
+    close(dq2, edq, 3e-2, 3e-2, "dq (o)"); close(dk2, edk, 3e-2, 3e-2, "dk (o)"); close(dv2, edv, 3e-2, 3e-2, "dv (o)")
 
 
 # ---------------------------------------------------------------- decoder assembly / loss / optimizer
