@@ -43,7 +43,18 @@ def linear_bwd(st: ParamStore, dy: Tensor, x: Tensor, W: nn.Parameter, b: Option
     dx = dy W[:, cols] (with optional fused epilogue) or None."""
     want_b = b is not None and b.requires_grad
     if W.requires_grad:       # bias gradient rides along in the wgrad launch (ones-tile MMA)
-        K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True, rowsum_out=st.grad(b) if want_b else None)
+        ws = st.wgrad_stream()
+        if ws is None:
+            K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True, rowsum_out=st.grad(b) if want_b else None)
+        else:
+            # Nothing in backward consumes dW / db, so the wgrad launch leaves the dgrad critical path: it is
+            # issued on a dedicated stream that is joined only at the end of backward.
+            ws.wait_stream(torch.cuda.current_stream())
+            dy.record_stream(ws)
+            x.record_stream(ws)
+            gw, gb = _w2d(st.grad(W), cols), (st.grad(b) if want_b else None)
+            with torch.cuda.stream(ws):
+                K.gemm(dy, x, False, False, out=gw, accumulate=True, rowsum_out=gb)
     elif want_b:
         K.colsum_bf16(dy, st.grad(b))
     if not need_dx:

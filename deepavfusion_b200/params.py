@@ -211,6 +211,18 @@ class ParamStore:
             self.join_side_streams(self.main_stream)
         torch.autograd.Variable._execution_engine.queue_callback(join)
 
+    def wgrad_stream(self):
+        """Dedicated stream for weight-gradient GEMMs (None on CPU tensors or with DAVF_WGRAD_STREAM=0)."""
+        ws = self.__dict__.get("_wgrad_stream", False)
+        if ws is False:
+            import os
+            ws = None
+            if self.flat_g.is_cuda and os.environ.get("DAVF_WGRAD_STREAM", "1") != "0" and os.environ.get("DAVF_STREAMS", "1") != "0":
+                ws = torch.cuda.Stream(self.flat_g.device)
+                self.side_streams.append(ws)
+            self.__dict__["_wgrad_stream"] = ws
+        return ws
+
     def join_side_streams(self, stream=None) -> None:
         """Make ``stream`` (default: the stream the last forward was issued on) wait for the side streams.
         The engine callback may run on an autograd worker thread whose *current* stream is not the caller's,

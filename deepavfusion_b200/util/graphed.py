@@ -14,6 +14,10 @@ import torch
 
 
 class GraphedTrainStep:
+    """Capture once, replay per step.  Drop references to the outputs (losses, predictions) of earlier EAGER
+    steps before constructing this object: they carry ``record_stream`` marks from the multi-stream forward, and
+    freeing such a tensor while a capture is in progress invalidates the capture."""
+
     def __init__(self, trainer, image_example: torch.Tensor, audio_example: torch.Tensor, warmup: int = 3,
                  capture_error_mode: str = "thread_local"):
         assert trainer.accum_iter == 1, "graph capture covers one full optimizer step (accum_iter == 1)"

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Kernel timeline of ONE graph-replayed training step (torch.profiler / CUPTI): per-stream busy time, span,
+and the largest gaps.  Run on the GPU box; writes gpurun_out/timeline_summary.txt."""
+import collections, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from deepavfusion_b200.util.graphed import GraphedTrainStep
+dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+trainer = bench.build_trainer(dev, False)
+img, aud = bench.synth_inputs(64, 1000, False)
+img, aud = img.to(dev), aud.to(dev)
+def _eager():
+    li, la, _, _ = trainer.model(img, aud); trainer.step(li + la)
+_eager()   # outputs of eager steps must not outlive the capture (see GraphedTrainStep docstring)
+g = GraphedTrainStep(trainer, img, aud, warmup=2)
+for _ in range(3): g(img, aud)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    g(img, aud)
+    torch.cuda.synchronize()
+os.makedirs("gpurun_out", exist_ok=True)
+prof.export_chrome_trace("gpurun_out/timeline.json")
+ev = json.load(open("gpurun_out/timeline.json"))["traceEvents"]
+ks = [e for e in ev if e.get("cat") == "kernel"]
+ks.sort(key=lambda e: e["ts"])
+t0 = ks[0]["ts"]; t1 = max(e["ts"] + e["dur"] for e in ks)
+out = [f"kernels {len(ks)}  span {(t1 - t0) / 1e3:.2f} ms"]
+by = collections.defaultdict(list)
+for e in ks: by[e["args"].get("stream")].append(e)
+for s, L in by.items():
+    busy = sum(e["dur"] for e in L)
+    out.append(f"stream {s}: {len(L)} kernels, busy {busy / 1e3:.2f} ms, first {(L[0]['ts'] - t0) / 1e3:.2f} last {(L[-1]['ts'] + L[-1]['dur'] - t0) / 1e3:.2f}")
+# machine occupancy over time: how much of the span has >=1 kernel running, and time with only 'small' kernels
+events = []
+for e in ks: events += [(e["ts"], 1), (e["ts"] + e["dur"], -1)]
+events.sort()
+cur = 0; last = t0; idle = 0.0
+for t, d in events:
+    if cur == 0: idle += t - last
+    cur += d; last = t
+out.append(f"time with no kernel running: {idle / 1e3:.2f} ms")
+# per-phase: find the adamw kernel and the first backward kernel (masked_mse bwd)
+def first(name):
+    for e in ks:
+        if name in e["name"]: return (e["ts"] - t0) / 1e3
+out.append(f"loss bwd starts at {first('masked_mse_kernel<true>')} ms, adamw at {first('adamw_kernel')} ms")
+agg = collections.defaultdict(float)
+for e in ks: agg[e["name"][:60]] += e["dur"]
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:14]: out.append(f"{v / 1e3:8.2f} ms  {k}")
+open("gpurun_out/timeline_summary.txt", "w").write("\n".join(out))
+print("\n".join(out))
