@@ -215,7 +215,7 @@ struct TileSched {
 // windows, gathered residuals, ...).  EPI >= 0: bit mask of the options below, fixed at compile time
 // for the six epilogues that carry > 90 % of the GEMM time, so that no flag tests, dead operand
 // prefetches or dead address arithmetic remain in the (instruction-bound) epilogue loop.
-enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_AUX = 8, EPI_RES = 16, EPI_BF16 = 32, EPI_RED = 64 };
+enum : int { EPI_BIAS = 1, EPI_GELU = 2, EPI_DGELU = 4, EPI_AUX = 8, EPI_RES = 16, EPI_BF16 = 32, EPI_RED = 64, EPI_ROWSUM = 128 };
 template <int EPI>
 struct EpiSel {
   static constexpr bool kStatic = EPI >= 0;
@@ -227,6 +227,7 @@ struct EpiSel {
   __device__ __forceinline__ static bool bf16(const EpiParams& p) { return kStatic ? (EPI & EPI_BF16) != 0 : p.out_bf16 != 0; }
   __device__ __forceinline__ static bool red(const EpiParams& p) { return kStatic ? (EPI & EPI_RED) != 0 : p.accumulate != 0; }
   __device__ __forceinline__ static bool remap(const EpiParams& p) { return kStatic ? false : (p.g > 0 || p.res_idx != nullptr); }
+  __device__ __forceinline__ static bool rowsum(const EpiParams& p) { return kStatic ? (EPI & EPI_ROWSUM) != 0 : p.rowsum_out != nullptr; }
 };
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN
@@ -244,17 +245,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool lead_cta = cta_rank == 0;
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
-  constexpr uint32_t TMEM_COLS = 512;               // two accumulator stages of BN columns (+ 2 x 16 row-sum columns when BN = 128)
+  constexpr uint32_t TMEM_COLS = 512;
+  // accumulator stages: two (epilogue of tile i overlaps the MMAs of tile i+1) unless the tile is 256 columns wide AND
+  // carries the 16 row-sum columns (wgrad + bias gradient): TMEM has 512 columns, so that case is single-buffered
+  constexpr bool kStaticRowsum = EPI >= 0 && (EPI & EPI_ROWSUM) != 0;
+  constexpr int NACC = (BN == 256 && kStaticRowsum) ? 1 : 2;
   constexpr uint32_t IDESC = make_idesc(BM * CG, BN, A_KMAJOR ? 0 : 1, B_KMAJOR ? 0 : 1);
-  constexpr uint32_t IDESC_ONES = make_idesc(BM, 16, A_KMAJOR ? 0 : 1, 0);
-  constexpr uint32_t ROWSUM_COL = 2 * BN;           // only used when BN == 128 (host enforces it)
+  constexpr uint32_t IDESC_ONES = make_idesc(BM * CG, 16, A_KMAJOR ? 0 : 1, 0);
+  constexpr uint32_t ROWSUM_COL = NACC * BN;        // row-sum columns follow the accumulator stages (BN = 256 only when NACC = 1)
+  static_assert(NACC * BN + NACC * 16 <= 512 || !kStaticRowsum, "TMEM overflow");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
   const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
   const uint32_t ones_base = stage_base + kStagingBytes;                  // 1024-byte aligned, kOnesBytes
   const uint32_t bar_base = ones_base + kOnesBytes;
-  const bool want_rowsum = ep.rowsum_out != nullptr;
+  const bool want_rowsum = EpiSel<EPI>::rowsum(ep);
   // barrier addresses: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -355,8 +361,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
         int m_blk, n_blk, sp, kb0, kb1;
         ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1u;
+        const int acc = local % NACC;
+        const uint32_t acc_phase = (local / NACC) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -378,8 +384,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint64_t adesc = adesc0 + (uint64_t)(k * A_STEP), bdesc = bdesc0 + (uint64_t)(k * B_STEP);
               if (CG == 2) umma_f16_2cta(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
               else umma_f16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-              if (CG == 1 && rowsum_tile)     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
-                umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (rowsum_tile) {     // D[:, 0:16] += A * ones^T  ->  every column holds sum_k A(m, k)
+                if (CG == 2) umma_f16_2cta(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
+                else umma_f16(tmem_base + ROWSUM_COL + acc * 16, adesc, ones_desc, IDESC_ONES, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
             }
             if (CG == 2) umma_commit_2cta(empty_bar(stage)); else umma_commit(empty_bar(stage));   // frees the smem slot(s) once these MMAs retire
           }
@@ -410,8 +418,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
       int m_blk, n_blk, sp, kb0, kb1;
       ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1u;
+      const int acc = local % NACC;
+      const uint32_t acc_phase = (local / NACC) & 1u;
       const int64_t m_base = (int64_t)m_blk * (BM * CG) + cta_rank * BM + quad * 32;
       // per-tile row bookkeeping for the 4 rows this lane touches in the coalesced phase
       int64_t out_off[4], res_off[4], aux_off[4];
@@ -447,7 +455,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (dbg && t == 0 && warp == 2 && lane == 0) dbg[4] = clock64();
-      if (CG == 1 && want_rowsum && n_blk == 0 && half == 0) {
+      if (want_rowsum && n_blk == 0 && half == 0) {
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
@@ -631,8 +639,9 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
 
 // run-time epilogue mask of a launch, or -1 if it needs the generic kernel
 static int epi_mask(const davf_gemm_args& a) {
-  if (a.g > 0 || a.res_idx || a.rowsum_out || a.debug_clocks) return -1;
+  if (a.g > 0 || a.res_idx || a.debug_clocks) return -1;
   int m = 0;
+  if (a.rowsum_out) m |= EPI_ROWSUM;
   if (a.bias) m |= EPI_BIAS;
   if (a.act == DAVF_ACT_GELU) m |= EPI_GELU;
   if (a.act == DAVF_ACT_DGELU) m |= EPI_DGELU;
@@ -647,7 +656,7 @@ static bool has_static_epi(const davf_gemm_args& a) {
   const int em = epi_mask(a);
   if (a.a_kmajor && a.b_kmajor) return em == (EPI_BIAS | EPI_BF16) || em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16) || em == (EPI_BIAS | EPI_RES);
   if (a.a_kmajor && !a.b_kmajor) return em == EPI_BF16 || em == (EPI_DGELU | EPI_BF16);
-  if (!a.a_kmajor && !a.b_kmajor) return em == EPI_RED;
+  if (!a.a_kmajor && !a.b_kmajor) return em == EPI_RED || em == (EPI_RED | EPI_ROWSUM);
   return false;
 }
 
@@ -664,8 +673,11 @@ static int launch_major(const davf_gemm_args& a, const CUtensorMap& ta, const CU
     if (em == EPI_BF16) return launch_cfg<BN, STAGES, true, false, EPI_BF16, CG>(ta, tb, ts, ep, st);
     if (em == (EPI_DGELU | EPI_BF16)) return launch_cfg<BN, STAGES, true, false, EPI_DGELU | EPI_BF16, CG>(ta, tb, ts, ep, st);
     if constexpr (CG == 1) return launch_cfg<BN, STAGES, true, false, -1, 1>(ta, tb, ts, ep, st);
-  } else if (!a.a_kmajor && !a.b_kmajor) {   // wgrad (row-sum launches take the generic 1-CTA kernel)
+  } else if (!a.a_kmajor && !a.b_kmajor) {   // wgrad, with or without the bias-gradient row sums
     if (em == EPI_RED) return launch_cfg<BN, STAGES, false, false, EPI_RED, CG>(ta, tb, ts, ep, st);
+    if constexpr (CG == 2 || BN == 128) {
+      if (em == (EPI_RED | EPI_ROWSUM)) return launch_cfg<BN, STAGES, false, false, EPI_RED | EPI_ROWSUM, CG>(ta, tb, ts, ep, st);
+    }
     if constexpr (CG == 1) return launch_cfg<BN, STAGES, false, false, -1, 1>(ta, tb, ts, ep, st);
   } else {
     if constexpr (CG == 1) return launch_cfg<BN, STAGES, false, true, -1, 1>(ta, tb, ts, ep, st);
@@ -682,8 +694,8 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
     int splits = a.split_k;
     if (splits <= 0) {   // auto: fill the machine when the caller allows atomic accumulation
       splits = 1;
-      if (a.accumulate) {
-        if (mn_tiles < units) splits = (int)((units + mn_tiles - 1) / mn_tiles);
+      if (a.accumulate) {      // split K so that the tiles fill (at most) one wave of CTAs / CTA pairs
+        if (mn_tiles < units) splits = (int)(units / mn_tiles);
         if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
       }
     }
