@@ -32,11 +32,9 @@ namespace davf {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
 constexpr int kStageCols = 16;                         // columns per epilogue chunk
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
-constexpr uint32_t kStagingBytes = kNumEpiWarps * 32 * kStagePitch * 4;
+__host__ __device__ constexpr uint32_t staging_bytes(int epi_warps) { return epi_warps * 32 * kStagePitch * 4; }
 constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
 constexpr uint32_t kSpinLimit = 4000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
 
@@ -234,8 +232,10 @@ struct EpiSel {
 // tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of B (BN/2 rows), the
 // MMA reads both halves, so the shared-memory fill traffic per FLOP halves (the 1-CTA kernel is bound by the
 // per-SM TMA fill rate, not by the tensor pipe).  TileSched m-blocks are 128*CG rows.
-template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// EW = number of epilogue warps (8, or 16 for the transcendental-heavy GELU / dGELU epilogues, which are
+// instruction-bound: EW/4 warps share a TMEM lane quadrant and split the tile's columns).
+template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                TileSched ts, EpiParams ep) {
   constexpr int BNL = BN / CG;                       // B rows staged by this CTA
@@ -258,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
   const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
-  const uint32_t ones_base = stage_base + kStagingBytes;                  // 1024-byte aligned, kOnesBytes
+  const uint32_t ones_base = stage_base + staging_bytes(EW);              // 1024-byte aligned, kOnesBytes
   const uint32_t bar_base = ones_base + kOnesBytes;
   const bool want_rowsum = EpiSel<EPI>::rowsum(ep);
   // barrier addresses: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem_ptr
@@ -279,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps * CG);     // the leader's barrier collects the epilogue warps of both CTAs
+      mbar_init(tempty_bar(a), EW * CG);     // the leader's barrier collects the epilogue warps of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -407,10 +407,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // chunk c is processed (and for the first chunk before the accumulator is even ready), so their
     // L2/HBM latency is off the critical path of this 10-warp, low-occupancy CTA.
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
-    const int half = (warp - 2) >> 2;          // which half of the tile's columns
+    const int half = (warp - 2) >> 2;          // which slice of the tile's columns (EW/4 slices)
+    constexpr int SLICE = BN / (EW / 4);       // columns per epilogue warp
     float* stg = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 32 * kStagePitch;
     const int rr = lane >> 2, cc = (lane & 3) * 4;   // coalesced phase: 4 lanes per row, 8 rows per iteration
-    constexpr int NCHUNK = BN / 2 / kStageCols;
+    constexpr int NCHUNK = SLICE / kStageCols;
     using F = EpiSel<EPI>;
     const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
     struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
@@ -440,7 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       const bool add_bias = has_bias && sp == 0;
       auto prefetch = [&](int c, Pre& pr) {
-        const int64_t n = (int64_t)n_blk * BN + half * (BN / 2) + c * kStageCols + cc;
+        const int64_t n = (int64_t)n_blk * BN + half * SLICE + c * kStageCols + cc;
         const bool nv = n < ep.N;
         pr.bias = (add_bias && nv) ? *reinterpret_cast<const float4*>(ep.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -463,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // below is unrolled by two with the buffers swapped, so no register copies (which would force a wait on
       // the in-flight loads) sit between chunks.
       auto process = [&](int c, const Pre& use, Pre& fill) {
-        const int col0 = half * (BN / 2) + c * kStageCols;
+        const int col0 = half * SLICE + c * kStageCols;
         float z[kStageCols];
         tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), z);
         if (c == NCHUNK - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp early
@@ -608,12 +609,17 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
-template <int BN, int STAGES, bool AK, bool BKM, int EPI, int CG>
+template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + kStagingBytes + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
+  // 16 epilogue warps for the GELU / dGELU epilogues of the CTA-pair kernel (one pipeline stage is traded for their staging)
+  constexpr bool kHeavy = EPI >= 0 && (EPI & (EPI_GELU | EPI_DGELU)) != 0 && CG == 2;
+  constexpr int EW = kHeavy ? 16 : 8;
+  constexpr int STAGES = kHeavy ? STAGES_ - 1 : STAGES_;
+  constexpr int kNumThreads = 64 + 32 * EW;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EW) + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG>;
+  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG, EW>;
   if (!attr_set) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
