@@ -109,18 +109,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 // ---------------------------------------------------------------------------------------------
-// forward: grid (ceil(Nq / 64), B*H), 128 threads; warp = 16 query rows
+// forward: grid (ceil(Nq / (16 NW)), B*H), NW warps; warp = 16 query rows (NW = 1 / 2 / 4 by problem size)
 // ---------------------------------------------------------------------------------------------
-template <int DQK, int DV>
-__global__ void __launch_bounds__(128) attn_mma_fwd_kernel(davf_attn_fwd_args a, int Nkp) {
+template <int DQK, int DV, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_mma_fwd_kernel(davf_attn_fwd_args a, int Nkp) {
   extern __shared__ __align__(16) uint8_t smem[];
-  uint16_t* Qs = reinterpret_cast<uint16_t*>(smem);            // [64][DQK+8]
-  uint16_t* Ks = Qs + 64 * (DQK + 8);                          // [Nkp][DQK+8]
+  constexpr int QT = NW * 16;                                  // query rows per CTA
+  uint16_t* Qs = reinterpret_cast<uint16_t*>(smem);            // [QT][DQK+8]
+  uint16_t* Ks = Qs + QT * (DQK + 8);                          // [Nkp][DQK+8]
   uint16_t* Vs = Ks + Nkp * (DQK + 8);                         // [Nkp][DV+8]
   const int bh = blockIdx.y, b = bh / a.H, h = bh - b * a.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * 64;
-  load_tile<DQK>(Qs, a.q + (int64_t)b * a.q_bs + (int64_t)q0 * a.q_rs + h * DQK, a.q_rs, min(64, a.Nq - q0), 64);
+  const int q0 = blockIdx.x * QT;
+  load_tile<DQK>(Qs, a.q + (int64_t)b * a.q_bs + (int64_t)q0 * a.q_rs + h * DQK, a.q_rs, min(QT, a.Nq - q0), QT);
   load_tile<DQK>(Ks, a.k + (int64_t)b * a.k_bs + h * DQK, a.k_rs, a.Nk, Nkp);
   load_tile<DV>(Vs, a.v + (int64_t)b * a.v_bs + h * DV, a.v_rs, a.Nk, Nkp);
   __syncthreads();
@@ -196,13 +197,13 @@ __global__ void __launch_bounds__(128) attn_mma_fwd_kernel(davf_attn_fwd_args a,
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: one CTA per (b, h), 256 threads (8 warps); Q, K, V, dO of the head in shared memory.
+// backward: one CTA per (b, h), NW warps (2 / 4 / 8 by problem size); Q, K, V, dO of the head in shared memory.
 //   phase A (warp = 16 query rows): pass 1  D_i = sum_j P_ij dP_ij ; pass 2  dQ = scale * dS K
 //   phase B (warp = 16 key rows):   dV = P^T dO ; dK = scale * dS^T Q      (transposed tiles recomputed)
 //   P = exp(scale S - lse), dP = dO V^T, dS = P (dP - D)
 // ---------------------------------------------------------------------------------------------
-template <int DQK, int DV>
-__global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a, int Nqp, int Nkp) {
+template <int DQK, int DV, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_args a, int Nqp, int Nkp) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint16_t* Qs = reinterpret_cast<uint16_t*>(smem);            // [Nqp][DQK+8]
   uint16_t* Ks = Qs + Nqp * (DQK + 8);                         // [Nkp][DQK+8]
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
   }
 
   // ---------------- phase A ----------------
-  for (int qt = warp; qt * 16 < Nq; qt += 8) {
+  for (int qt = warp; qt * 16 < Nq; qt += NW) {
     uint32_t aq[DQK / 16][4], ado[DV / 16][4];
     load_a_frags<DQK>(aq, Qs, qt * 16, lane);
     load_a_frags<DV>(ado, dOs, qt * 16, lane);
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
   __syncthreads();
 
   // ---------------- phase B ----------------
-  for (int kt = warp; kt * 16 < Nk; kt += 8) {
+  for (int kt = warp; kt * 16 < Nk; kt += NW) {
     uint32_t ak[DQK / 16][4], av[DV / 16][4];
     load_a_frags<DQK>(ak, Ks, kt * 16, lane);
     load_a_frags<DV>(av, Vs, kt * 16, lane);
@@ -361,35 +362,49 @@ __global__ void __launch_bounds__(256) attn_mma_bwd_kernel(davf_attn_bwd_args a,
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-template <int DQK, int DV>
-static int launch_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
+template <int DQK, int DV, int NW>
+static int launch_fwd_nw(const davf_attn_fwd_args& a, cudaStream_t st) {
   const int Nkp = round_up(a.Nk, CH);
-  const size_t smem = (size_t)(64 + Nkp) * (DQK + 8) * 2 + (size_t)Nkp * (DV + 8) * 2;
-  auto kern = attn_mma_fwd_kernel<DQK, DV>;
+  constexpr int QT = NW * 16;
+  const size_t smem = (size_t)(QT + Nkp) * (DQK + 8) * 2 + (size_t)Nkp * (DV + 8) * 2;
+  auto kern = attn_mma_fwd_kernel<DQK, DV, NW>;
   static size_t configured = 0;
   if (smem > configured) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid((a.Nq + 63) / 64, a.B * a.H);
-  kern<<<grid, 128, smem, st>>>(a, Nkp);
+  dim3 grid((a.Nq + QT - 1) / QT, a.B * a.H);
+  kern<<<grid, NW * 32, smem, st>>>(a, Nkp);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
-
 template <int DQK, int DV>
-static int launch_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
+static int launch_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
+  if (a.Nq <= 16) return launch_fwd_nw<DQK, DV, 1>(a, st);      // fusion-token attentions: 8 / 16 queries
+  if (a.Nq <= 32) return launch_fwd_nw<DQK, DV, 2>(a, st);
+  return launch_fwd_nw<DQK, DV, 4>(a, st);
+}
+
+template <int DQK, int DV, int NW>
+static int launch_bwd_nw(const davf_attn_bwd_args& a, cudaStream_t st) {
   const int Nqp = round_up(a.Nq, CH), Nkp = round_up(a.Nk, CH);
   const size_t smem = (size_t)(Nqp + Nkp) * (DQK + 8) * 2 + (size_t)(Nqp + Nkp) * (DV + 8) * 2 + (size_t)2 * Nqp * 4;
-  auto kern = attn_mma_bwd_kernel<DQK, DV>;
+  auto kern = attn_mma_bwd_kernel<DQK, DV, NW>;
   static size_t configured = 0;
   if (smem > configured) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<a.B * a.H, 256, smem, st>>>(a, Nqp, Nkp);
+  kern<<<a.B * a.H, NW * 32, smem, st>>>(a, Nqp, Nkp);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
+}
+template <int DQK, int DV>
+static int launch_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
+  const int n = a.Nq > a.Nk ? a.Nq : a.Nk;
+  if (n <= 32) return launch_bwd_nw<DQK, DV, 2>(a, st);         // one or two 16-row tiles per phase
+  if (n <= 128) return launch_bwd_nw<DQK, DV, 4>(a, st);
+  return launch_bwd_nw<DQK, DV, 8>(a, st);
 }
 
 int attn_simt_fwd(const davf_attn_fwd_args* a, cudaStream_t st);
