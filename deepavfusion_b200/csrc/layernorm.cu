@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap 
     *reinterpret_cast<float4*>(my + a.D + col) = db[i];
   }
   __syncthreads();
-  for (int c4 = threadIdx.x; c4 < 2 * a.D / 4; c4 += blockDim.x) {
+  const int ncol4 = 2 * a.D / 4;
+  for (int i = threadIdx.x; i < ncol4; i += blockDim.x) {
+    // rotate the column order per CTA: CTAs finish together, and same-address reductions serialise in L2
+    const int c4 = (i + (int)blockIdx.x * 61) % ncol4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int w = 0; w < wpb; ++w) {
       const float4 v = *reinterpret_cast<const float4*>(sm_red + (size_t)w * 2 * a.D + c4 * 4);
