@@ -178,7 +178,9 @@ def gemm_roofline(trace, peaks, reps=5):
         return cache[k]
     calls = []
     flops = 0.0
-    for t in trace:
+
+    def problem(t):
+        nonlocal flops
         M, N, Kd = t["M"], t["N"], t["K"]
         a = buf("a", (M if t["a_kmajor"] else Kd, t["lda"]), bf16)[:, :(Kd if t["a_kmajor"] else M)]
         b = buf("b", (N if t["b_kmajor"] else Kd, t["ldb"]), bf16)[:, :(Kd if t["b_kmajor"] else N)]
@@ -186,19 +188,27 @@ def gemm_roofline(trace, peaks, reps=5):
         kw = dict(bias=buf("bias", (N,), torch.float32) if t["bias"] else None, act=t["act"], want_aux=t["aux"],
                   res=buf("r", (M, N), torch.float32) if t["res"] else None,
                   res_idx=buf("ri", (M,), torch.int64) if t["res_idx"] else None,
-                  out=out, accumulate=t["accumulate"])
+                  out=out, accumulate=t["accumulate"],
+                  rowsum_out=buf("rs", (M,), torch.float32) if t.get("rowsum") else None)
         if t["act"] == K.ACT_DGELU:
             kw["aux_in"] = buf("h", (M, N), bf16)
-        calls.append((a, b, t["a_kmajor"], t["b_kmajor"], kw))
         flops += 2.0 * M * N * Kd
-    for a, b, ak, bk, kw in calls:          # warm-up
-        K.gemm(a, b, ak, bk, **kw)
+        return (a, b, t["a_kmajor"], t["b_kmajor"]), kw
+    for t in trace:              # one entry per LAUNCH: a single problem or a grouped launch of several
+        calls.append([problem(u) for u in t["group"]] if "group" in t else problem(t))
+
+    def replay():
+        for c in calls:
+            if isinstance(c, list):
+                K.gemm_grouped(c)
+            else:
+                K.gemm(*c[0], **c[1])
+    replay()                     # warm-up
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for a, b, ak, bk, kw in calls:
-            K.gemm(a, b, ak, bk, **kw)
+        replay()
     e1.record()
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 1e3 / reps

@@ -95,6 +95,7 @@ SIGNATURES = {
     "davf_layernorm_fwd": (i, [C.POINTER(LnFwdArgs), vp]),
     "davf_layernorm_bwd": (i, [C.POINTER(LnBwdArgs), vp]),
     "davf_gemm": (i, [C.POINTER(GemmArgs), vp]),
+    "davf_gemm_grouped": (i, [C.POINTER(GemmArgs), i, vp]),
     "davf_attention_fwd": (i, [C.POINTER(AttnFwdArgs), vp]),
     "davf_attention_bwd": (i, [C.POINTER(AttnBwdArgs), vp]),
     "davf_decoder_assemble_fwd": (i, [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),

@@ -36,6 +36,7 @@ constexpr int kStageCols = 16;                         // columns per epilogue c
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
 __host__ __device__ constexpr uint32_t staging_bytes(int epi_warps) { return epi_warps * 32 * kStagePitch * 4; }
 constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
+constexpr int kMaxGroup = 6;                          // problems per grouped launch (kernel parameter block ~2.6 KB)
 constexpr uint32_t kSpinLimit = 4000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------
@@ -209,6 +210,18 @@ struct TileSched {
   }
 };
 
+// Kernel parameters: NG independent GEMM problems served by ONE launch (NG = 1: the ordinary case).  The
+// tile index space is the concatenation of the problems' tiles (tile_end = exclusive prefix sums; unused
+// slots repeat the last value), so the many tiny GEMMs of a fusion block (M = 512 rows, 24 tiles each,
+// latency-bound at ~10 us per launch) share one launch, one prologue and one wave of CTAs.
+template <int NG>
+struct GemmGroup {
+  CUtensorMap ta[NG], tb[NG];
+  EpiParams ep[NG];
+  TileSched ts[NG];
+  int tile_end[NG];
+};
+
 // Compile-time epilogue specialisation.  EPI < 0: every option is a run-time flag (rare shapes: row
 // windows, gathered residuals, ...).  EPI >= 0: bit mask of the options below, fixed at compile time
 // for the six epilogues that carry > 90 % of the GEMM time, so that no flag tests, dead operand
@@ -234,10 +247,18 @@ struct EpiSel {
 // per-SM TMA fill rate, not by the tensor pipe).  TileSched m-blocks are 128*CG rows.
 // EW = number of epilogue warps (8, or 16 for the transcendental-heavy GELU / dGELU epilogues, which are
 // instruction-bound: EW/4 warps share a TMEM lane quadrant and split the tile's columns).
-template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG, int EW>
+template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG, int EW, int NG>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               TileSched ts, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
+  static_assert(NG == 1 || (EPI < 0 && CG == 1), "grouped launches use the run-time-flag 1-CTA kernel");
+  // tile t of the launch -> problem p, tile tl of that problem
+  auto locate = [&](int t, int& p, int& tl) {
+    p = 0; tl = t;
+    if (NG > 1) {
+      while (p < NG - 1 && t >= gp.tile_end[p]) ++p;
+      if (p) tl = t - gp.tile_end[p - 1];
+    }
+  };
   constexpr int BNL = BN / CG;                       // B rows staged by this CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BNL * BK * 2;
@@ -260,7 +281,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
   const uint32_t ones_base = stage_base + staging_bytes(EW);              // 1024-byte aligned, kOnesBytes
   const uint32_t bar_base = ones_base + kOnesBytes;
-  const bool want_rowsum = EpiSel<EPI>::rowsum(ep);
+  bool want_rowsum = false;
+#pragma unroll
+  for (int p = 0; p < NG; ++p) want_rowsum |= EpiSel<EPI>::rowsum(gp.ep[p]);
   // barrier addresses: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -271,8 +294,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+#pragma unroll
+    for (int p = 0; p < NG; ++p) {
+      if (p == 0 || gp.tile_end[p] > gp.tile_end[p - 1]) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gp.ta[p])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&gp.tb[p])) : "memory");
+      }
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -303,8 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
-  const int num_tiles = ts.num_tiles();
-  long long* dbg = (CG == 1 && ep.debug_clocks && blockIdx.x == 0) ? ep.debug_clocks : nullptr;   // optional timeline probe of CTA 0
+  const int num_tiles = gp.tile_end[NG - 1];
+  long long* dbg = (NG == 1 && CG == 1 && gp.ep[0].debug_clocks && blockIdx.x == 0) ? gp.ep[0].debug_clocks : nullptr;   // optional timeline probe of CTA 0
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0) {
@@ -319,8 +347,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (CG == 2) tma_load_2d_2cta(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
       };
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int m_blk, n_blk, sp, kb0, kb1;
-        ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+        int p, tl, m_blk, n_blk, sp, kb0, kb1;
+        locate(t, p, tl);
+        gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+        const CUtensorMap* tmap_a = &gp.ta[p];
+        const CUtensorMap* tmap_b = &gp.tb[p];
         const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM;      // this CTA's rows of A
         const int n0 = n_blk * BN + (int)cta_rank * BNL;             // this CTA's rows of B
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -331,16 +362,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (leader) {
             if (lead_cta) mbar_expect_tx(full_bar(stage), STAGE_BYTES * CG);   // bytes of both CTAs land on the leader's barrier
             if (A_KMAJOR) {
-              tma(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+              tma(sa, tmap_a, full_bar(stage), kb * BK, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma(sa + j * 8192, &tmap_a, full_bar(stage), m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma(sa + j * 8192, tmap_a, full_bar(stage), m0 + j * 64, kb * BK);
             }
             if (B_KMAJOR) {
-              tma(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+              tma(sb, tmap_b, full_bar(stage), kb * BK, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BNL / 64; ++j) tma(sb + j * 8192, &tmap_b, full_bar(stage), n0 + j * 64, kb * BK);
+              for (int j = 0; j < BNL / 64; ++j) tma(sb + j * 8192, tmap_b, full_bar(stage), n0 + j * 64, kb * BK);
             }
           }
           __syncwarp();
@@ -359,14 +390,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int local = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
-        int m_blk, n_blk, sp, kb0, kb1;
-        ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+        int p, tl, m_blk, n_blk, sp, kb0, kb1;
+        locate(t, p, tl);
+        gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
         const int acc = local % NACC;
         const uint32_t acc_phase = (local / NACC) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        const bool rowsum_tile = want_rowsum && n_blk == 0;
+        const bool rowsum_tile = EpiSel<EPI>::rowsum(gp.ep[p]) && n_blk == 0;
         const uint64_t ones_desc = make_smem_desc(ones_base, 16, 1024);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -413,12 +445,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int rr = lane >> 2, cc = (lane & 3) * 4;   // coalesced phase: 4 lanes per row, 8 rows per iteration
     constexpr int NCHUNK = SLICE / kStageCols;
     using F = EpiSel<EPI>;
-    const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
     struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
     int local = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
-      int m_blk, n_blk, sp, kb0, kb1;
-      ts.decode(t, m_blk, n_blk, sp, kb0, kb1);
+      int p, tl, m_blk, n_blk, sp, kb0, kb1;
+      locate(t, p, tl);
+      gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+      const EpiParams& ep = gp.ep[p];
+      const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
       const int acc = local % NACC;
       const uint32_t acc_phase = (local / NACC) & 1u;
       const int64_t m_base = (int64_t)m_blk * (BM * CG) + cta_rank * BM + quad * 32;
@@ -456,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (dbg && t == 0 && warp == 2 && lane == 0) dbg[4] = clock64();
-      if (want_rowsum && n_blk == 0 && half == 0) {
+      if (F::rowsum(ep) && n_blk == 0 && half == 0) {
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m_base + lane < ep.M) atomicAdd(ep.rowsum_out + m_base + lane, rs);
       }
@@ -609,8 +643,8 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
-template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
+template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG, int NG = 1>
+static int launch_group(const GemmGroup<NG>& gp, cudaStream_t st) {
   // 16 epilogue warps for the GELU / dGELU epilogues of the CTA-pair kernel (one pipeline stage is traded for their staging)
   constexpr bool kHeavy = EPI >= 0 && (EPI & (EPI_GELU | EPI_DGELU)) != 0 && CG == 2;
   constexpr int EW = kHeavy ? 16 : 8;
@@ -619,12 +653,12 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EW) + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG, EW>;
+  auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG, EW, NG>;
   if (!attr_set) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int tiles = ts.m_tiles * ts.n_tiles * ts.splits;
+  const int tiles = gp.tile_end[NG - 1];
   const int clusters = tiles < kNumSMs / CG ? tiles : kNumSMs / CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
@@ -638,9 +672,17 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
-  DAVF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ts, ep));
+  DAVF_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
   g_launches.fetch_add(1);
   return DAVF_OK;
+}
+
+template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
+  GemmGroup<1> gp;
+  gp.ta[0] = ta; gp.tb[0] = tb; gp.ep[0] = ep; gp.ts[0] = ts;
+  gp.tile_end[0] = ts.m_tiles * ts.n_tiles * ts.splits;
+  return launch_group<BN, STAGES_, AK, BKM, EPI, CG, 1>(gp, st);
 }
 
 // run-time epilogue mask of a launch, or -1 if it needs the generic kernel
@@ -748,6 +790,51 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   if (rc) return rc;
   if (bn == 256) return launch_major<256, 4, 1>(a, ta, tb, ts, st);
   return launch_major<128, 6, 1>(a, ta, tb, ts, st);
+}
+
+// ---- grouped launch: up to kMaxGroup problems of ONE operand-layout class in one launch (1-CTA 128 x 128 tiles,
+// run-time-flag epilogue).  Accumulating problems (wgrad) are split along K so that the group fills about one wave.
+int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) {
+  GemmGroup<kMaxGroup> gp;
+  memset(&gp, 0, sizeof(gp));
+  int64_t mn_total = 0;
+  for (int p = 0; p < count; ++p) mn_total += ((a[p].M + BM - 1) / BM) * ((a[p].N + 127) / 128);
+  int end = 0, rc;
+  for (int p = 0; p < kMaxGroup; ++p) {
+    if (p >= count) {                 // unused slot: no tiles; keep valid (never dereferenced) descriptors
+      gp.ta[p] = gp.ta[0]; gp.tb[p] = gp.tb[0]; gp.ep[p] = gp.ep[0]; gp.ts[p] = gp.ts[0];
+      gp.tile_end[p] = end;
+      continue;
+    }
+    const davf_gemm_args& g = a[p];
+    const int kb_total = (int)((g.K + BK - 1) / BK);
+    const int m_tiles = (int)((g.M + BM - 1) / BM), n_tiles = (int)((g.N + 127) / 128);
+    int splits = g.split_k > 0 ? g.split_k : 1;
+    if (g.split_k <= 0 && g.accumulate && mn_total < kNumSMs) {
+      splits = (int)(kNumSMs / mn_total);
+      if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+    }
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    const int per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+    gp.ts[p] = TileSched{m_tiles, n_tiles, splits, kb_total, per};
+    if (g.a_kmajor) rc = get_tensor_map(g.a, g.K, g.M, g.lda, BM, &gp.ta[p]);
+    else rc = get_tensor_map(g.a, g.M, g.K, g.lda, BK, &gp.ta[p]);
+    if (rc) return rc;
+    if (g.b_kmajor) rc = get_tensor_map(g.b, g.K, g.N, g.ldb, 128, &gp.tb[p]);
+    else rc = get_tensor_map(g.b, g.N, g.K, g.ldb, BK, &gp.tb[p]);
+    if (rc) return rc;
+    gp.ep[p] = make_epi(g);
+    gp.ep[p].debug_clocks = nullptr;
+    end += m_tiles * n_tiles * splits;
+    gp.tile_end[p] = end;
+  }
+  const bool ak = a[0].a_kmajor != 0, bk = a[0].b_kmajor != 0;
+  if (ak && bk) return launch_group<128, 6, true, true, -1, 1, kMaxGroup>(gp, st);
+  if (ak && !bk) return launch_group<128, 6, true, false, -1, 1, kMaxGroup>(gp, st);
+  if (!ak && !bk) return launch_group<128, 6, false, false, -1, 1, kMaxGroup>(gp, st);
+  return launch_group<128, 6, false, true, -1, 1, kMaxGroup>(gp, st);
 }
 
 int gemm_set_2cta(int on) { g_allow_2cta.store(on ? 1 : 0); return 0; }

@@ -266,15 +266,97 @@ class LayerNormFn(torch.autograd.Function):
 # a4  fusion-token attention of FusionBlock_FactorizedAVInteractions (fusion_blocks.py:235-283)
 #     out = LN_mm(xmm) + cat(proj(pair_attn), attn_v, attn_a)
 # --------------------------------------------------------------------------------------------
+class _Lin:
+    """One Linear of a grouped launch, described by raw views: ``w`` bf16 [N, K] (possibly a column slice of a
+    stacked weight), ``b`` f32 bias or None, ``gw`` / ``gb`` the gradient views they accumulate into (None =
+    frozen)."""
+    __slots__ = ("w", "b", "gw", "gb")
+
+    def __init__(self, w, b=None, gw=None, gb=None):
+        self.w, self.b, self.gw, self.gb = w, b, gw, gb
+
+
+def _lin_of(st: ParamStore, W: nn.Parameter, b: Optional[nn.Parameter]) -> "_Lin":
+    return _Lin(st.lowp(W), None if b is None else b.data, st.grad(W) if W.requires_grad else None,
+                st.grad(b) if (b is not None and b.requires_grad) else None)
+
+
+def group_fwd(items):
+    """items = [(x, _Lin, epilogue kwargs)]: independent forward Linears in one launch."""
+    return K.gemm_grouped([((x, l.w, True, True), dict(bias=l.b, **kw)) for x, l, kw in items])
+
+
+def group_bwd(st: ParamStore, items):
+    """items = [(dy, x, _Lin, dgrad epilogue kwargs or None)]: the wgrad (+ bias gradient) launches of all items
+    go out as one grouped launch on the wgrad stream, the dgrad launches as one grouped launch on the
+    current stream.  Returns the dx list (None where no dgrad was requested)."""
+    wg = [((dy, x, False, False), dict(out=l.gw, accumulate=True, rowsum_out=l.gb)) for dy, x, l, _ in items if l.gw is not None]
+    for dy, x, l, _ in items:
+        if l.gw is None and l.gb is not None:
+            K.colsum_bf16(dy, l.gb)
+    if wg:
+        ws = st.wgrad_stream()
+        if ws is None:
+            K.gemm_grouped(wg)
+        else:
+            ws.wait_stream(torch.cuda.current_stream())
+            for (dy, x, _, _), _kw in wg:
+                dy.record_stream(ws)
+                x.record_stream(ws)
+            with torch.cuda.stream(ws):
+                K.gemm_grouped(wg)
+    dg = [(i, ((dy, l.w, True, False), kw)) for i, (dy, x, l, kw) in enumerate(items) if kw is not None]
+    out = [None] * len(items)
+    for (i, _), r in zip(dg, K.gemm_grouped([c for _, c in dg])):
+        out[i] = r
+    return out
+
+
 class FusionAttnFn(torch.autograd.Function):
     """The dense pair attention (:245-258) is evaluated in its exactly-equivalent factorised form
     (SURVEY.md 7.1-2): k(xva_ij) = Wk1 v_i + Wk2 a_j + bk  =>  softmax over the 8x8 pairs is the
     outer product of two 8-way softmaxes, and the value sum splits the same way; xva is never
-    materialised and the k / v projections shrink 8x."""
+    materialised and the k / v projections shrink 8x.
+
+    Launch structure: the block's ~20 small Linears have M = 512 .. 3136 rows and are latency-bound one by
+    one, and the fusion block is the critical path of every encoder layer (the modality blocks run beside it
+    on other streams).  Independent Linears therefore share grouped launches (``K.gemm_grouped``), and the
+    pair-attention k / v Linears -- same input, weights stacked in the flat buffer -- are one GEMM."""
+
+    @staticmethod
+    def _idx(m, B, F, off, n_tok, device):
+        """Row indices of out[b, off:off+n_tok] in the [B*F, D] layout (cached: no per-step arange kernels)."""
+        cache = m.__dict__.setdefault("_idx_cache", {})
+        key = (B, F, off, n_tok, str(device))
+        t = cache.get(key)
+        if t is None:
+            t = (torch.arange(B, device=device).view(B, 1) * F + off + torch.arange(n_tok, device=device).view(1, n_tok)).reshape(-1)
+            cache[key] = t
+        return t
+
+    @staticmethod
+    def _lins(m):
+        st: ParamStore = m.store
+        D = m.v_w.shape[0]
+        kv_lp, kv_g = st.stacked(m.k_w, m.v_w)                       # [qk + D, 2D]
+        train = m.k_w.requires_grad
+        assert m.v_w.requires_grad == train
+        if m.k_b is not None:
+            kvb_lp, kvb_g = st.stacked(m.k_b, m.v_b)                 # bf16 shadow unused: the bias is read in f32
+            k0, _ = st.span(st.index_of(m.k_b))
+            kvb = st.flat_p[k0:k0 + kvb_g.numel()]
+            kvb_g = kvb_g if m.k_b.requires_grad else None
+        else:
+            kvb, kvb_g = None, None
+        pair_v = _Lin(kv_lp[:, :D], kvb, kv_g[:, :D] if train else None, kvb_g)      # bias on the v side only
+        pair_a = _Lin(kv_lp[:, D:], None, kv_g[:, D:] if train else None, None)
+        return SimpleNamespace(
+            q_v=_lin_of(st, m.attn_v.q_w, m.attn_v.q_b), kv_v=_lin_of(st, m.attn_v.kv_w, m.attn_v.kv_b), proj_v=_lin_of(st, m.attn_v.proj_w, m.attn_v.proj_b),
+            q_a=_lin_of(st, m.attn_a.q_w, m.attn_a.q_b), kv_a=_lin_of(st, m.attn_a.kv_w, m.attn_a.kv_b), proj_a=_lin_of(st, m.attn_a.proj_w, m.attn_a.proj_b),
+            q2=_lin_of(st, m.q_w, m.q_b), pair_v=pair_v, pair_a=pair_a, proj=_lin_of(st, m.proj_w, m.proj_b))
 
     @staticmethod
     def forward(ctx, xmm: Tensor, xv: Tensor, xa: Tensor, anchor: Tensor, m: SimpleNamespace):
-        st: ParamStore = m.store
         xmm, xv, xa = xmm.contiguous(), xv.contiguous(), xa.contiguous()
         B, F, D = xmm.shape
         nmm, nv, na = m.tkns
@@ -283,42 +365,37 @@ class FusionAttnFn(torch.autograd.Function):
         qk = m.q_w.shape[0]
         dq = qk // H
         scale = hd ** -0.5                                                          # fusion_blocks.py:220-222
+        L = FusionAttnFn._lins(m)
         seg = [0, nmm, nmm + nv, F]
         mm_b, mm_f, mean_m, rstd_m = K.layernorm_fwd(xmm, None, m.n_mm_w.data, m.n_mm_b.data, m.eps, True, True, seg)
         m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
         xv_n, _, mean_v, rstd_v = K.layernorm_fwd(xv, None, m.n_img_w.data, m.n_img_b.data, m.eps)
         xa_n, _, mean_a, rstd_a = K.layernorm_fwd(xa, None, m.n_aud_w.data, m.n_aud_b.data, m.eps)
         out = torch.empty(B * F, D, dtype=torch.float32, device=xmm.device)
+        Nv, Na = xv_n.shape[0] // B, xa_n.shape[0] // B
 
-        def cross(tok, ctx_n, c, n_tok, off):
-            """CrossAttention (fusion_blocks.py:46-59) for n_tok aggregation tokens; writes
-            out[b, off:off+n_tok] = LN_mm(xmm)[b, off:...] + proj(.) and returns the bf16 proj output."""
-            Nc = ctx_n.shape[0] // B
-            q = linear_fwd(st, tok, c.q_w, c.q_b)                                   # [B*n_tok, D]
-            kv = linear_fwd(st, ctx_n, c.kv_w, c.kv_b)                              # [B*Nc, 2D]
-            kv5 = kv.view(B, Nc, 2, H, hd)
-            o, lse = K.attention_fwd(q.view(B, n_tok, H, hd), kv5[:, :, 0], kv5[:, :, 1], scale)
-            _, pr = linear_fwd(st, o.view(B * n_tok, D), c.proj_w, c.proj_b, want_aux=True, res=mm_f, out=out,
-                               window=(n_tok, F, off))
-            return q, kv, o, lse, pr
-
-        qv, kvv, ov, lse_v, pv = cross(mv, xv_n, m.attn_v, nv, nmm)
-        qa, kva, oa, lse_a, pa = cross(ma, xa_n, m.attn_a, na, nmm + nv)
-        # factorised pair attention
-        q2 = linear_fwd(st, m2, m.q_w, m.q_b)                                       # [B*nmm, qk]
-        k_v = linear_fwd(st, pv, m.k_w, m.k_b, cols=(0, D))                          # [B*nv, qk]  (bias on the v side)
-        v_v = linear_fwd(st, pv, m.v_w, m.v_b, cols=(0, D))                          # [B*nv, D]
-        k_a = linear_fwd(st, pa, m.k_w, None, cols=(D, 2 * D))
-        v_a = linear_fwd(st, pa, m.v_w, None, cols=(D, 2 * D))
+        # every Linear that only needs the normed inputs: CrossAttention q / kv of both modalities (:46-52) + pair q (:252)
+        qv, kvv, qa, kva, q2 = group_fwd([(mv, L.q_v, {}), (xv_n, L.kv_v, {}), (ma, L.q_a, {}), (xa_n, L.kv_a, {}), (m2, L.q2, {})])
+        kvv5, kva5 = kvv.view(B, Nv, 2, H, hd), kva.view(B, Na, 2, H, hd)
+        ov, lse_v = K.attention_fwd(qv.view(B, nv, H, hd), kvv5[:, :, 0], kvv5[:, :, 1], scale)
+        oa, lse_a = K.attention_fwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], scale)
+        # out[b, off:off+n] = LN_mm(xmm)[b, off:...] + proj(.) ; the bf16 proj outputs feed the pair attention
+        (_, pv), (_, pa) = group_fwd([
+            (ov.view(B * nv, D), L.proj_v, dict(want_aux=True, res=mm_f, out=out, window=(nv, F, nmm))),
+            (oa.view(B * na, D), L.proj_a, dict(want_aux=True, res=mm_f, out=out, window=(na, F, nmm + nv)))])
+        # factorised pair attention: [k | v] of each side in one GEMM against the stacked weight
+        kv2v, kv2a = group_fwd([(pv, L.pair_v, {}), (pa, L.pair_a, {})])            # [B*nv, qk + D], [B*na, qk + D]
         q2v = q2.view(B, nmm, H, dq)
-        o2, lse2v = K.attention_fwd(q2v, k_v.view(B, nv, H, dq), v_v.view(B, nv, H, hd), scale)
-        _, lse2a = K.attention_fwd(q2v, k_a.view(B, na, H, dq), v_a.view(B, na, H, hd), scale, out=o2, accumulate=True)
+        k_v, v_v = kv2v.view(B, nv, qk + D)[:, :, :qk].unflatten(2, (H, dq)), kv2v.view(B, nv, qk + D)[:, :, qk:].unflatten(2, (H, hd))
+        k_a, v_a = kv2a.view(B, na, qk + D)[:, :, :qk].unflatten(2, (H, dq)), kv2a.view(B, na, qk + D)[:, :, qk:].unflatten(2, (H, hd))
+        o2, lse2v = K.attention_fwd(q2v, k_v, v_v, scale)
+        _, lse2a = K.attention_fwd(q2v, k_a, v_a, scale, out=o2, accumulate=True)
         o2 = o2.view(B * nmm, D)
-        linear_fwd(st, o2, m.proj_w, m.proj_b, res=mm_f, out=out, window=(nmm, F, 0))
+        K.gemm(o2, L.proj.w, bias=L.proj.b, res=mm_f, out=out, window=(nmm, F, 0))
         ctx.m = m
         ctx.save_for_backward(xmm, xv, xa, mean_m, rstd_m, mean_v, rstd_v, mean_a, rstd_a, mm_b, xv_n, xa_n,
                               qv, kvv, ov, lse_v, pv, qa, kva, oa, lse_a, pa,
-                              q2, k_v, v_v, k_a, v_a, lse2v, lse2a, o2)
+                              q2, kv2v, kv2a, lse2v, lse2a, o2)
         return out.view(B, F, D)
 
     @staticmethod
@@ -327,14 +404,17 @@ class FusionAttnFn(torch.autograd.Function):
         st: ParamStore = m.store
         (xmm, xv, xa, mean_m, rstd_m, mean_v, rstd_v, mean_a, rstd_a, mm_b, xv_n, xa_n,
          qv, kvv, ov, lse_v, pv, qa, kva, oa, lse_a, pa,
-         q2, k_v, v_v, k_a, v_a, lse2v, lse2a, o2) = ctx.saved_tensors
+         q2, kv2v, kv2a, lse2v, lse2a, o2) = ctx.saved_tensors
         dout = dout.contiguous()
         B, F, D = dout.shape
         nmm, nv, na = m.tkns
         H = m.heads
         hd = D // H
-        dq = m.q_w.shape[0] // H
+        qk = m.q_w.shape[0]
+        dq = qk // H
         scale = hd ** -0.5
+        L = FusionAttnFn._lins(m)
+        Nv, Na = xv_n.shape[0] // B, xa_n.shape[0] // B
         d2 = dout.view(B * F, D)
         m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
         dseg = torch.empty_like(mm_b)                                               # d LN_mm(xmm), segment-major bf16
@@ -342,38 +422,37 @@ class FusionAttnFn(torch.autograd.Function):
 
         # ---- pair attention ----
         dr2 = K.cast_rows_bf16(d2, B * nmm, nmm, F, 0)
-        do2 = linear_bwd(st, dr2, o2, m.proj_w, m.proj_b).view(B, nmm, H, hd)
+        (do2,) = group_bwd(st, [(dr2, o2, L.proj, {})])
+        do2 = do2.view(B, nmm, H, hd)
         dq2 = torch.empty_like(q2)
-        dk_v, dv_v, dk_a, dv_a = torch.empty_like(k_v), torch.empty_like(v_v), torch.empty_like(k_a), torch.empty_like(v_a)
+        dkv2v, dkv2a = torch.empty_like(kv2v), torch.empty_like(kv2a)
+
+        def split(t, n):
+            t3 = t.view(B, n, qk + D)
+            return t3[:, :, :qk].unflatten(2, (H, dq)), t3[:, :, qk:].unflatten(2, (H, hd))
         q2v = q2.view(B, nmm, H, dq)
-        K.attention_bwd(q2v, k_v.view(B, nv, H, dq), v_v.view(B, nv, H, hd), do2, lse2v, scale,
-                        dq2.view(B, nmm, H, dq), dk_v.view(B, nv, H, dq), dv_v.view(B, nv, H, hd))
-        K.attention_bwd(q2v, k_a.view(B, na, H, dq), v_a.view(B, na, H, hd), do2, lse2a, scale,
-                        dq2.view(B, nmm, H, dq), dk_a.view(B, na, H, dq), dv_a.view(B, na, H, hd), accumulate_dq=True)
-        linear_bwd(st, dq2, m2, m.q_w, m.q_b, out=dm2)
-
-        def pair_side(dk, dv, p_tok, cols, kb, vb, n_tok, off):
-            """d proj-output of one aggregation group = residual path + k path + v path."""
-            idx = (torch.arange(B, device=dout.device).view(B, 1) * F + off + torch.arange(n_tok, device=dout.device).view(1, n_tok)).reshape(-1)
-            t = linear_bwd(st, dk, p_tok, m.k_w, kb, cols=cols, res=d2, res_idx=idx, out_dtype=torch.float32)
-            return linear_bwd(st, dv, p_tok, m.v_w, vb, cols=cols, res=t, out_dtype=torch.bfloat16)
-
-        dpv = pair_side(dk_v, dv_v, pv, (0, D), m.k_b, m.v_b, nv, nmm)
-        dpa = pair_side(dk_a, dv_a, pa, (D, 2 * D), None, None, na, nmm + nv)
+        (k_v, v_v), (k_a, v_a) = split(kv2v, nv), split(kv2a, na)
+        (dk_v, dv_v), (dk_a, dv_a) = split(dkv2v, nv), split(dkv2a, na)
+        K.attention_bwd(q2v, k_v, v_v, do2, lse2v, scale, dq2.view(B, nmm, H, dq), dk_v, dv_v)
+        K.attention_bwd(q2v, k_a, v_a, do2, lse2a, scale, dq2.view(B, nmm, H, dq), dk_a, dv_a, accumulate_dq=True)
+        # d proj-output of each aggregation group = residual path (rows of dout) + [dk | dv] through the stacked weight
+        idx_v = FusionAttnFn._idx(m, B, F, nmm, nv, dout.device)
+        idx_a = FusionAttnFn._idx(m, B, F, nmm + nv, na, dout.device)
+        _, dpv, dpa = group_bwd(st, [(dq2, m2, L.q2, dict(out=dm2)),
+                                     (dkv2v, pv, L.pair_v, dict(res=d2, res_idx=idx_v)),
+                                     (dkv2a, pa, L.pair_a, dict(res=d2, res_idx=idx_a))])
 
         # ---- the two cross attentions ----
-        def cross_bwd(dp, tok, ctx_n, c, q, kv, o, lse, n_tok, d_tok_out):
-            Nc = ctx_n.shape[0] // B
-            do = linear_bwd(st, dp, o.view(B * n_tok, D), c.proj_w, c.proj_b).view(B, n_tok, H, hd)
-            dqc, dkv = torch.empty_like(q), torch.empty_like(kv)
-            kv5, dkv5 = kv.view(B, Nc, 2, H, hd), dkv.view(B, Nc, 2, H, hd)
-            K.attention_bwd(q.view(B, n_tok, H, hd), kv5[:, :, 0], kv5[:, :, 1], do, lse, scale,
-                            dqc.view(B, n_tok, H, hd), dkv5[:, :, 0], dkv5[:, :, 1])
-            linear_bwd(st, dqc, tok, c.q_w, c.q_b, out=d_tok_out)
-            return linear_bwd(st, dkv, ctx_n, c.kv_w, c.kv_b)                       # [B*Nc, D] bf16
-
-        dxv_n = cross_bwd(dpv, mv, xv_n, m.attn_v, qv, kvv, ov, lse_v, nv, dmv)
-        dxa_n = cross_bwd(dpa, ma, xa_n, m.attn_a, qa, kva, oa, lse_a, na, dma)
+        do_v, do_a = group_bwd(st, [(dpv, ov.view(B * nv, D), L.proj_v, {}), (dpa, oa.view(B * na, D), L.proj_a, {})])
+        dqv, dkvv, dqa, dkva = torch.empty_like(qv), torch.empty_like(kvv), torch.empty_like(qa), torch.empty_like(kva)
+        kvv5, dkvv5 = kvv.view(B, Nv, 2, H, hd), dkvv.view(B, Nv, 2, H, hd)
+        kva5, dkva5 = kva.view(B, Na, 2, H, hd), dkva.view(B, Na, 2, H, hd)
+        K.attention_bwd(qv.view(B, nv, H, hd), kvv5[:, :, 0], kvv5[:, :, 1], do_v.view(B, nv, H, hd), lse_v, scale,
+                        dqv.view(B, nv, H, hd), dkvv5[:, :, 0], dkvv5[:, :, 1])
+        K.attention_bwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], do_a.view(B, na, H, hd), lse_a, scale,
+                        dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1])
+        _, _, dxv_n, dxa_n = group_bwd(st, [(dqv, mv, L.q_v, dict(out=dmv)), (dqa, ma, L.q_a, dict(out=dma)),
+                                            (dkvv, xv_n, L.kv_v, {}), (dkva, xa_n, L.kv_a, {})])
 
         dxv, _ = K.layernorm_bwd(xv, None, m.n_img_w.data, mean_v, rstd_v, dxv_n, None, None, None,
                                  st.grad(m.n_img_w), st.grad(m.n_img_b))

@@ -185,18 +185,13 @@ def layernorm_bwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor,
 GEMM_TRACE = None     # bench.py sets this to a list to record the (M, N, K, majors, epilogue) of every launch
 
 
-def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
-         bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
-         res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
-         out: Optional[Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False,
-         window: Optional[Tuple[int, int, int]] = None, split_k: int = 0, rowsum_out: Optional[Tensor] = None,
-         debug_clocks: Optional[Tensor] = None):
-    """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of davf.h.
-
-    ``a`` / ``b`` are the STORED 2-D bf16 matrices (row-major views, stride(1) == 1):
-    K-major operand: stored [rows, K]; MN-major operand: stored [K, rows].
-    ``window`` = (g, G, off): output (and residual) row of m is (m//g)*G + off + m%g; ``out`` must
-    then be given.  Returns ``out`` or ``(out, aux)`` when ``want_aux``."""
+def _gemm_args(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
+               bias: Optional[Tensor] = None, act: int = ACT_NONE, want_aux: bool = False, aux_in: Optional[Tensor] = None,
+               res: Optional[Tensor] = None, res_idx: Optional[Tensor] = None,
+               out: Optional[Tensor] = None, out_dtype=torch.bfloat16, accumulate: bool = False,
+               window: Optional[Tuple[int, int, int]] = None, split_k: int = 0, rowsum_out: Optional[Tensor] = None,
+               debug_clocks: Optional[Tensor] = None):
+    """Checks one GEMM problem and fills its C-ABI argument block.  Returns (args, result, trace record)."""
     _need(a, torch.bfloat16, "a", contiguous=False); _need(b, torch.bfloat16, "b", contiguous=False)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     if a_kmajor:
@@ -244,13 +239,50 @@ def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, *,
         assert rowsum_out.numel() == M
     if debug_clocks is not None:
         ga.debug_clocks = _need(debug_clocks, torch.int64, "debug_clocks").data_ptr()
+    rec = None
     if GEMM_TRACE is not None:
-        GEMM_TRACE.append(dict(M=M, N=N, K=K, a_kmajor=a_kmajor, b_kmajor=b_kmajor, lda=a.stride(0), ldb=b.stride(0),
-                               bias=bias is not None, act=act, aux=want_aux, res=res is not None, res_idx=res_idx is not None,
-                               out_bf16=out.dtype == torch.bfloat16, accumulate=accumulate, window=window, ldo=out.stride(-2),
-                               rowsum=rowsum_out is not None))
+        rec = dict(M=M, N=N, K=K, a_kmajor=a_kmajor, b_kmajor=b_kmajor, lda=a.stride(0), ldb=b.stride(0),
+                   bias=bias is not None, act=act, aux=want_aux, res=res is not None, res_idx=res_idx is not None,
+                   out_bf16=out.dtype == torch.bfloat16, accumulate=accumulate, window=window, ldo=out.stride(-2),
+                   rowsum=rowsum_out is not None)
+    return ga, ((out, aux) if want_aux else out), rec
+
+
+def gemm(a: Tensor, b: Tensor, a_kmajor: bool = True, b_kmajor: bool = True, **kw):
+    """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of davf.h.
+
+    ``a`` / ``b`` are the STORED 2-D bf16 matrices (row-major views, stride(1) == 1):
+    K-major operand: stored [rows, K]; MN-major operand: stored [K, rows].
+    ``window`` = (g, G, off): output (and residual) row of m is (m//g)*G + off + m%g; ``out`` must
+    then be given.  Returns ``out`` or ``(out, aux)`` when ``want_aux``.  Keyword options: see ``_gemm_args``."""
+    ga, result, rec = _gemm_args(a, b, a_kmajor, b_kmajor, **kw)
+    if rec is not None:
+        GEMM_TRACE.append(rec)
     check(_cabi.lib().davf_gemm(C.byref(ga), _stream()), "davf_gemm")
-    return (out, aux) if want_aux else out
+    return result
+
+
+GEMM_MAX_GROUP = 6
+
+
+def gemm_grouped(problems: Sequence[Tuple[tuple, dict]]):
+    """``problems`` = [((a, b, a_kmajor, b_kmajor), kwargs), ...]: independent GEMMs of ONE operand-layout class
+    launched as one kernel (davf_gemm_grouped); longer lists are cut into launches of GEMM_MAX_GROUP.  Returns the
+    list of per-problem results (as ``gemm`` would)."""
+    results = []
+    for i0 in range(0, len(problems), GEMM_MAX_GROUP):
+        chunk = problems[i0:i0 + GEMM_MAX_GROUP]
+        arr = (_cabi.GemmArgs * len(chunk))()
+        recs = []
+        for j, (pos, kw) in enumerate(chunk):
+            ga, result, rec = _gemm_args(*pos, **kw)
+            arr[j] = ga
+            results.append(result)
+            recs.append(rec)
+        if GEMM_TRACE is not None:
+            GEMM_TRACE.append(dict(group=recs))
+        check(_cabi.lib().davf_gemm_grouped(arr, len(chunk), _stream()), "davf_gemm_grouped")
+    return results
 
 
 # --------------------------------------------------------------------------------------------

@@ -59,21 +59,40 @@ def forward_order_key(name: str):
     return (9, 0, 0)
 
 
+_PAIR_KV = {"attn.k.weight": 1, "attn.v.weight": 2, "attn.k.bias": 3, "attn.v.bias": 4}
+
+
+def _pair_kv_rank(name: str) -> int:
+    """Inside a fusion block the pair-attention ``k`` and ``v`` Linears (fusion_blocks.py:228-229) read the
+    same input, so their weights (and biases) are stored back to back: [k.weight; v.weight] is then ONE
+    [qk + D, 2D] matrix and k / v become a single GEMM in forward, dgrad and wgrad (``ParamStore.stacked``)."""
+    if _FUS.match(name):
+        for suffix, r in _PAIR_KV.items():
+            if name.endswith(suffix):
+                return r
+    return 0
+
+
 class ParamStore:
     def __init__(self, module: nn.Module):
         named = [(n, p) for n, p in module.named_parameters()]
         assert named, "module has no parameters"
         dev = named[0][1].device
-        order = sorted(range(len(named)), key=lambda i: (forward_order_key(named[i][0]), i))
+        order = sorted(range(len(named)), key=lambda i: (forward_order_key(named[i][0]), _pair_kv_rank(named[i][0]), i))
         self.names: List[str] = []
         self.params: List[nn.Parameter] = []
         self.offsets: List[int] = []
         off = 0
+        end_prev, rank_prev = 0, 0
         for i in order:
             n, p = named[i]
             assert p.dtype == torch.float32, f"{n}: master parameters must be f32"
+            rank = _pair_kv_rank(n)
+            if rank in (2, 4) and rank_prev == rank - 1 and end_prev % 8 == 0:
+                off = end_prev           # v directly behind k (no alignment gap): [k; v] is one stacked tensor
             self.names.append(n); self.params.append(p); self.offsets.append(off)
-            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+            end_prev, rank_prev = off + p.numel(), rank
+            off = (end_prev + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
         self.device = dev
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -149,6 +168,20 @@ class ParamStore:
 
     def lowp(self, p: nn.Parameter) -> torch.Tensor:
         return self._lp[self._index[id(p)]]
+
+    def stacked(self, p1: nn.Parameter, p2: nn.Parameter):
+        """(bf16 shadow, gradient) views of ``[p1; p2]`` as one tensor stacked along dim 0.  Requires the two
+        parameters to be adjacent in the flat buffers (see ``_pair_kv_rank``) with equal trailing shapes."""
+        k1, k2 = self._index[id(p1)], self._index[id(p2)]
+        o1, o2 = self.offsets[k1], self.offsets[k2]
+        if o2 != o1 + p1.numel() or p1.shape[1:] != p2.shape[1:]:
+            raise RuntimeError(f"parameters {self.names[k1]} / {self.names[k2]} are not stacked in the flat buffer "
+                               f"(offsets {o1}+{p1.numel()} vs {o2}); build the ParamStore over the whole model")
+        shape = (p1.shape[0] + p2.shape[0],) + tuple(p1.shape[1:])
+        n = p1.numel() + p2.numel()
+        if (p1.requires_grad and not self._attached(p1, k1)) or (p2.requires_grad and not self._attached(p2, k2)):
+            self.ensure_grads(force=True)
+        return self.flat_lp[o1:o1 + n].view(shape), self.flat_g[o1:o1 + n].view(shape)
 
     # -- gradients ------------------------------------------------------------------------------
     def _attached(self, p: nn.Parameter, k: int) -> bool:

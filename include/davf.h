@@ -154,6 +154,14 @@ typedef struct {
 } davf_gemm_args;
 int davf_gemm(const davf_gemm_args* a, davf_stream_t s);
 
+/* Grouped launch: `count` (1..DAVF_GEMM_MAX_GROUP) INDEPENDENT problems of one operand-layout class (same a_kmajor /
+ * b_kmajor) in a single kernel launch; results are identical to `count` davf_gemm calls.  Serves the many small
+ * Linears of one fusion block that have no data dependence on each other: CrossAttention q / kv of both modalities
+ * and the pair-attention q (fusion_blocks.py:46-52,235-252), their projections (:58,:262), and the matching dgrad /
+ * wgrad launches of backward, which are latency-bound when launched one by one (M = 512 rows). */
+#define DAVF_GEMM_MAX_GROUP 6
+int davf_gemm_grouped(const davf_gemm_args* a, int count, davf_stream_t s);
+
 /* ---- K6/K7/K8/K11: fused attention ----------------------------------------------------------
  * Replaces F.scaled_dot_product_attention in timm Attention (encoder d=64, decoder d=32) and the
  * explicit softmax(q k^T * scale) v of fusion_blocks.py:53-57,254-258.

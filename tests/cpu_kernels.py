@@ -170,6 +170,10 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, *, bias=None, act=ACT_NONE, want_au
     return (out, aux) if want_aux else out
 
 
+def gemm_grouped(problems):
+    return [gemm(*pos, **kw) for pos, kw in problems]
+
+
 def attention_fwd(q, k, v, scale, out=None, accumulate=False):
     qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3)
     s = qf @ kf.transpose(-1, -2) * scale

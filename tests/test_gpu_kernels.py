@@ -198,6 +198,43 @@ for two in ([1, 0] if impl == 0 else [0]):
         K.gemm(dy, a, False, False, out=gw, accumulate=True)
         check(f'{{tag}} wgrad red {{N}}x{{Kd}}x{{M}}', gw, 1 + dy.float().t() @ a.float(), 1e-2, 1e-1 * (M / 768) ** 0.5)
 K.set_gemm_2cta(True)
+# grouped launches: independent problems of one layout class in ONE kernel == the same problems one by one
+F_ = 32
+def group_case(tag, shapes, ak, bk, mode):
+    probs, refs = [], []
+    for j, (M, N, Kd) in enumerate(shapes):
+        a = rnd(*((M, Kd) if ak else (Kd, M)), seed=300 + j, dtype=bf16)
+        b = rnd(*((N, Kd) if bk else (Kd, N)), seed=310 + j, dtype=bf16) * 0.05
+        kw, ekw = {{}}, {{}}
+        if mode == 'fwd':
+            if j % 2 == 0:
+                bias = rnd(N, seed=320 + j); kw['bias'] = bias; ekw['bias'] = bias.cpu()
+            if j == 1:
+                res = rnd(M // 8 * F_, N, seed=330)
+                kw.update(res=res, out=torch.zeros(M // 8 * F_, N, device='cuda'), window=(8, F_, 16), want_aux=True)
+                ekw.update(res=res.cpu(), out=torch.zeros(M // 8 * F_, N), window=(8, F_, 16), want_aux=True)
+        elif mode == 'dgrad':
+            if j == 0:
+                res = rnd(M, N, seed=331); kw.update(res=res, out_dtype=torch.float32); ekw.update(res=res.cpu(), out_dtype=torch.float32)
+        else:
+            kw.update(out=torch.ones(M, N, device='cuda'), accumulate=True); ekw.update(out=torch.ones(M, N), accumulate=True)
+            if j != 1:
+                kw['rowsum_out'] = torch.zeros(M, device='cuda'); ekw['rowsum_out'] = torch.zeros(M)
+        probs.append(((a, b, ak, bk), kw)); refs.append(((a.cpu(), b.cpu(), ak, bk), ekw))
+    got = K.gemm_grouped(probs)
+    for j, (g, (pos, ekw)) in enumerate(zip(got, refs)):
+        e = E.gemm(*pos, **ekw)
+        Kd = shapes[j][2]
+        tol = dict(rtol=1e-2, atol=1e-1 * (Kd / 768) ** 0.5) if mode == 'wgrad' else {{}}
+        if isinstance(g, tuple):
+            check(f'{{tag}}[{{j}}] out', g[0], e[0], **tol); check(f'{{tag}}[{{j}}] aux', g[1], e[1], **tol)
+        else:
+            check(f'{{tag}}[{{j}}]', g, e, **tol)
+        if 'rowsum_out' in probs[j][1]:
+            check(f'{{tag}}[{{j}}] rowsum', probs[j][1]['rowsum_out'], ekw['rowsum_out'], 1e-2, 1e-1 * (Kd / 768) ** 0.5)
+group_case('group fwd', [(512, 768, 768), (512, 768, 768), (3136, 1536, 768), (1216, 1536, 768), (512, 192, 768)], True, True, 'fwd')
+group_case('group dgrad', [(512, 768, 960), (512, 768, 960), (40, 768, 192)], True, False, 'dgrad')
+group_case('group wgrad', [(768, 768, 512), (1536, 768, 3136), (192, 768, 512), (768, 768, 512), (960, 768, 512), (768, 768, 1216), (768, 72, 512)], False, False, 'wgrad')
 torch.cuda.synchronize()
 print('FAILS', fails)
 sys.exit(1 if fails else 0)

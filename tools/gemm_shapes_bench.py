@@ -29,7 +29,13 @@ for key, (t, n) in groups.items():
 rows.sort(key=lambda r: -r[0])
 tot = sum(r[0] for r in rows)
 print(f"total GEMM time/step {tot*1e3:.2f} ms over {sum(r[2] for r in rows)} launches, {len(rows)} signatures")
-for tt, sec, n, t in rows[:45]:
+for tt, sec, n, t in rows[:70]:
+    if "group" in t:
+        fl = sum(2.0 * u["M"] * u["N"] * u["K"] for u in t["group"])
+        u0 = t["group"][0]
+        maj = ("K" if u0["a_kmajor"] else "MN") + "/" + ("K" if u0["b_kmajor"] else "MN")
+        print(f"{tt*1e3:7.3f} ms  n={n:3d}  {sec*1e6:7.1f} us  {fl/sec/1e12:7.1f} TF/s  GROUP {maj} " + " ".join(f"{u['M']}x{u['N']}x{u['K']}" for u in t["group"]))
+        continue
     fl = 2.0 * t["M"] * t["N"] * t["K"]
     maj = ("K" if t["a_kmajor"] else "MN") + "/" + ("K" if t["b_kmajor"] else "MN")
     flags = "".join(c for c, on in (("b", t["bias"]), ("G", t["act"] == 1), ("D", t["act"] == 2), ("x", t["aux"]), ("r", t["res"]), ("A", t["accumulate"]), ("s", t.get("rowsum"))) if on)
