@@ -105,6 +105,14 @@ __device__ __forceinline__ float quad_max(float v) {
   return v;
 }
 
+// 2^x on the MUFU pipe with no range fix-up code (exp2f without fast-math costs 2 FMUL + FSETP per call; the
+// arguments here are <= 0 up to rounding, and flush-to-zero of tiny probabilities is harmless)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -141,27 +149,37 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_fwd_kernel(davf_attn_fwd_arg
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
     mma_nmajor<DQK>(s, qf, Ks, c0, lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (c0 + CH <= a.Nk) {               // full chunk: no key masks
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int col = c0 + nt * 8 + 2 * t;
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = (col + (e & 1)) < a.Nk;
-        s[nt][e] = ok ? s[nt][e] * sl : -INFINITY;
+        for (int e = 0; e < 4; ++e) s[nt][e] *= sl;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = c0 + nt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = (col + (e & 1)) < a.Nk;
+          s[nt][e] = ok ? s[nt][e] * sl : -INFINITY;
+        }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
     }
     const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
-    const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+    const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
     m0 = mn0; m1 = mn1;
     l0 *= al0; l1 *= al1;
 #pragma unroll
     for (int i = 0; i < DV / 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
-      s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+      s[nt][0] = ex2(s[nt][0] - m0); s[nt][1] = ex2(s[nt][1] - m0);
+      s[nt][2] = ex2(s[nt][2] - m1); s[nt][3] = ex2(s[nt][3] - m1);
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }
@@ -263,18 +281,23 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_arg
         for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
         mma_nmajor<DQK>(s, aq, Ks, c0, lane);
         mma_nmajor<DV>(dp, ado, Vs, c0, lane);
+        // Padded key columns (rows >= Nk of the K / V tiles are zero): P is masked to 0 there, in the last chunk only.
+        const bool partial = c0 + CH > Nk;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          const int col = c0 + nt * 8 + 2 * t;
-          const bool ok0 = col < Nk, ok1 = col + 1 < Nk;
-          const float p0 = ok0 ? exp2f(s[nt][0] * sl - L0) : 0.f, p1 = ok1 ? exp2f(s[nt][1] * sl - L0) : 0.f;
-          const float p2 = ok0 ? exp2f(s[nt][2] * sl - L1) : 0.f, p3 = ok1 ? exp2f(s[nt][3] * sl - L1) : 0.f;
+          float p0 = ex2(fmaf(s[nt][0], sl, -L0)), p1 = ex2(fmaf(s[nt][1], sl, -L0));
+          float p2 = ex2(fmaf(s[nt][2], sl, -L1)), p3 = ex2(fmaf(s[nt][3], sl, -L1));
+          if (partial) {
+            const int col = c0 + nt * 8 + 2 * t;
+            const bool ok0 = col < Nk, ok1 = col + 1 < Nk;
+            p0 = ok0 ? p0 : 0.f; p1 = ok1 ? p1 : 0.f; p2 = ok0 ? p2 : 0.f; p3 = ok1 ? p3 : 0.f;
+          }
           if (pass == 0) {
             D0 += p0 * dp[nt][0] + p1 * dp[nt][1];
             D1 += p2 * dp[nt][2] + p3 * dp[nt][3];
-          } else {
-            s[nt][0] = p0 * (dp[nt][0] - D0) * a.scale; s[nt][1] = p1 * (dp[nt][1] - D0) * a.scale;
-            s[nt][2] = p2 * (dp[nt][2] - D1) * a.scale; s[nt][3] = p3 * (dp[nt][3] - D1) * a.scale;
+          } else {       // dS without the softmax scale: it is applied once to the dQ accumulators
+            s[nt][0] = p0 * (dp[nt][0] - D0); s[nt][1] = p1 * (dp[nt][1] - D0);
+            s[nt][2] = p2 * (dp[nt][2] - D1); s[nt][3] = p3 * (dp[nt][3] - D1);
           }
         }
         if (pass == 1) {
@@ -293,13 +316,13 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_arg
           const int col = nt * 8 + 2 * t;
           if (r0 < Nq) {
             uint32_t* p = reinterpret_cast<uint32_t*>(qb + (int64_t)r0 * a.dq_rs + col);
-            float x = dq[nt][0], y = dq[nt][1];
+            float x = dq[nt][0] * a.scale, y = dq[nt][1] * a.scale;
             if (a.accumulate_dq) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
             *p = pack_bf16x2(x, y);
           }
           if (r1 < Nq) {
             uint32_t* p = reinterpret_cast<uint32_t*>(qb + (int64_t)r1 * a.dq_rs + col);
-            float x = dq[nt][2], y = dq[nt][3];
+            float x = dq[nt][2] * a.scale, y = dq[nt][3] * a.scale;
             if (a.accumulate_dq) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
             *p = pack_bf16x2(x, y);
           }
@@ -325,16 +348,17 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_arg
       for (int i = 0; i < 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
       mma_nmajor<DQK>(st, ak, Qs, c0, lane);        // S^T tile: rows = keys, cols = queries
       mma_nmajor<DV>(dpt, av, dOs, c0, lane);       // dP^T tile
+      // Padded query columns need no masks: their dO rows are zero (dV += P^T dO, dP = 0) and D = 0, so dS = 0;
+      // their lse is 0 and their Q row is zero, so P = 1 stays finite.
       float pt[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int qc = c0 + nt * 8 + 2 * t;
-        const bool ok0 = qc < Nq, ok1 = qc + 1 < Nq;
-        const float La = Ls[qc], Lb = Ls[qc + 1], Da = Ds[qc], Db = Ds[qc + 1];
-        pt[nt][0] = ok0 ? exp2f(st[nt][0] * sl - La) : 0.f; pt[nt][1] = ok1 ? exp2f(st[nt][1] * sl - Lb) : 0.f;
-        pt[nt][2] = ok0 ? exp2f(st[nt][2] * sl - La) : 0.f; pt[nt][3] = ok1 ? exp2f(st[nt][3] * sl - Lb) : 0.f;
-        st[nt][0] = pt[nt][0] * (dpt[nt][0] - Da) * a.scale; st[nt][1] = pt[nt][1] * (dpt[nt][1] - Db) * a.scale;
-        st[nt][2] = pt[nt][2] * (dpt[nt][2] - Da) * a.scale; st[nt][3] = pt[nt][3] * (dpt[nt][3] - Db) * a.scale;
+        const float2 L = *reinterpret_cast<const float2*>(Ls + qc), Dd = *reinterpret_cast<const float2*>(Ds + qc);
+        pt[nt][0] = ex2(fmaf(st[nt][0], sl, -L.x)); pt[nt][1] = ex2(fmaf(st[nt][1], sl, -L.y));
+        pt[nt][2] = ex2(fmaf(st[nt][2], sl, -L.x)); pt[nt][3] = ex2(fmaf(st[nt][3], sl, -L.y));
+        st[nt][0] = pt[nt][0] * (dpt[nt][0] - Dd.x); st[nt][1] = pt[nt][1] * (dpt[nt][1] - Dd.y);
+        st[nt][2] = pt[nt][2] * (dpt[nt][2] - Dd.x); st[nt][3] = pt[nt][3] * (dpt[nt][3] - Dd.y);
       }
       uint32_t fa[4][4];
       c_to_a(fa, pt);
@@ -348,8 +372,8 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_arg
 #pragma unroll
     for (int nt = 0; nt < DQK / 8; ++nt) {
       const int col = nt * 8 + 2 * t;
-      if (r0 < Nk) *reinterpret_cast<uint32_t*>(kb + (int64_t)r0 * a.dk_rs + col) = pack_bf16x2(dk[nt][0], dk[nt][1]);
-      if (r1 < Nk) *reinterpret_cast<uint32_t*>(kb + (int64_t)r1 * a.dk_rs + col) = pack_bf16x2(dk[nt][2], dk[nt][3]);
+      if (r0 < Nk) *reinterpret_cast<uint32_t*>(kb + (int64_t)r0 * a.dk_rs + col) = pack_bf16x2(dk[nt][0] * a.scale, dk[nt][1] * a.scale);
+      if (r1 < Nk) *reinterpret_cast<uint32_t*>(kb + (int64_t)r1 * a.dk_rs + col) = pack_bf16x2(dk[nt][2] * a.scale, dk[nt][3] * a.scale);
     }
 #pragma unroll
     for (int nt = 0; nt < DV / 8; ++nt) {
@@ -371,6 +395,7 @@ static int launch_fwd_nw(const davf_attn_fwd_args& a, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
   dim3 grid((a.Nq + QT - 1) / QT, a.B * a.H);
@@ -393,6 +418,8 @@ static int launch_bwd_nw(const davf_attn_bwd_args& a, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // without this the driver picks a carve-out that fits ONE 84 KB decoder CTA per SM (ncu: occupancy limit 1)
+    DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
   kern<<<a.B * a.H, NW * 32, smem, st>>>(a, Nqp, Nkp);

@@ -94,6 +94,14 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
+// gelu(x) and gelu'(x) from one evaluation of the Gaussian terms (x may alias g)
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  float cdf, e;
+  gauss_terms(x, cdf, e);
+  dg = fmaf(x * 0.39894228040143268f, e, cdf);
+  g = x * cdf;
+}
+
 // block-wide sum for blockDim.x <= 1024 (multiple of 32); scratch >= 32 floats
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -51,18 +51,19 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, int64_t m, int6
       const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
-    if (p.aux_out) {
-      uint2 o;
-      o.x = pack_bf16x2(v.x, v.y);
-      o.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(p.aux_out + m * p.ldaux + n) = o;
-    }
+    float4 ax = v;                                   // what aux_out receives: z, or gelu'(z) next to a GELU
     if (p.act == DAVF_ACT_GELU) {
-      v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+      gelu_both(v.x, v.x, ax.x); gelu_both(v.y, v.y, ax.y); gelu_both(v.z, v.z, ax.z); gelu_both(v.w, v.w, ax.w);
     } else if (p.act == DAVF_ACT_DGELU) {
       const uint2 u = *reinterpret_cast<const uint2*>(p.aux_in + m * p.ldaux + n);
       const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-      v.x *= dgelu_erf(lo.x); v.y *= dgelu_erf(lo.y); v.z *= dgelu_erf(hi.x); v.w *= dgelu_erf(hi.y);
+      v.x *= lo.x; v.y *= lo.y; v.z *= hi.x; v.w *= hi.y;
+    }
+    if (p.aux_out) {
+      uint2 o;
+      o.x = pack_bf16x2(ax.x, ax.y);
+      o.y = pack_bf16x2(ax.z, ax.w);
+      *reinterpret_cast<uint2*>(p.aux_out + m * p.ldaux + n) = o;
     }
     if (p.res) {
       const float4 r = *reinterpret_cast<const float4*>(p.res + rrow * p.ldres + n);

@@ -35,6 +35,18 @@ constexpr int UMMA_K = 16;
 constexpr int kStageCols = 16;                         // columns per epilogue chunk
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
 __host__ __device__ constexpr uint32_t staging_bytes(int epi_warps) { return epi_warps * 32 * kStagePitch * 4; }
+__host__ __device__ constexpr bool direct_epi(int epi) {   // bf16-output epilogues that store straight from registers (no staging)
+  return epi >= 0 && (epi & 32) != 0 && (epi & (16 | 64 | 128)) == 0;
+}
+constexpr uint32_t kTmaBox = 4096;                     // one TMA box of the direct epilogue: 32 rows x 128 B (64 bf16), SW128
+__host__ __device__ constexpr uint32_t staging_bytes(int epi, int epi_warps) { return direct_epi(epi) ? epi_warps * 2u * kTmaBox : staging_bytes(epi_warps); }
+__host__ __device__ constexpr uint32_t ones_bytes(int epi) { return direct_epi(epi) ? 0u : 2048u; }   // no row sums on the direct path
+// pipeline depth: what the caller asks for, capped by what fits next to the epilogue staging in 227 KB
+__host__ __device__ constexpr int fit_stages(int want, int epi, int ew, int bn, int cg) {
+  const int stage = 128 * 64 * 2 + (bn / cg) * 64 * 2;
+  const int avail = 232448 - 1024 - 16 - 8 * (2 * want + 5 + ew) - (int)ones_bytes(epi) - (int)staging_bytes(epi, ew);
+  return avail / stage < want ? avail / stage : want;
+}
 constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
 constexpr int kMaxGroup = 6;                          // problems per grouped launch (kernel parameter block ~2.6 KB)
 constexpr uint32_t kSpinLimit = 4000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
@@ -156,6 +168,57 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Asynchronous form: the load is issued here, the registers are valid after tmem_ld_wait(v).  The wait names the
+// registers as in/out operands so that neither nvcc nor ptxas moves a use of them above it.
+__device__ __forceinline__ void tmem_ld_32x32b_x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+// 256-bit global accesses (sm_100: LDG / STG .ENL2.256): one full 32-byte sector per lane, so the
+// "one output row per lane" register layout of tcgen05.ld stores without any shared-memory transposition.
+__device__ __forceinline__ void stg_256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ldg_256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+
+// TMA store of one box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float tmem_ld_32x32b_x1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
@@ -217,6 +280,7 @@ struct TileSched {
 template <int NG>
 struct GemmGroup {
   CUtensorMap ta[NG], tb[NG];
+  CUtensorMap tc, taux;              // direct (TMA) epilogue only: out / aux_out-or-aux_in as [M][N] bf16, box {64, 32}
   EpiParams ep[NG];
   TileSched ts[NG];
   int tile_end[NG];
@@ -279,8 +343,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
   const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
-  const uint32_t ones_base = stage_base + staging_bytes(EW);              // 1024-byte aligned, kOnesBytes
-  const uint32_t bar_base = ones_base + kOnesBytes;
+  const uint32_t ones_base = stage_base + staging_bytes(EPI, EW);              // 1024-byte aligned, kOnesBytes
+  const uint32_t bar_base = ones_base + ones_bytes(EPI);
   bool want_rowsum = false;
 #pragma unroll
   for (int p = 0; p < NG; ++p) want_rowsum |= EpiSel<EPI>::rowsum(gp.ep[p]);
@@ -290,6 +354,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  auto aux_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5 + w); };     // direct epilogue: TMA loads of the saved gelu'
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -309,10 +374,11 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EW * CG);     // the leader's barrier collects the epilogue warps of both CTAs
     }
+    for (int w = 0; w < EW; ++w) mbar_init(aux_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (want_rowsum) {      // bf16 1.0 everywhere: layout-agnostic B operand
-    for (uint32_t i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < ones_bytes(EPI) / 4; i += blockDim.x)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(ones_base + 4 * i), "r"(0x3F803F80u) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
   }
@@ -431,6 +497,106 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
         if (dbg && t == 0 && leader) dbg[3] = clock64();
       }
     }
+  } else if constexpr (direct_epi(EPI)) {
+    // ===================== TMA-store epilogue (bf16 outputs: bias / GELU / x gelu') =====================
+    // tcgen05.ld hands every lane 64 consecutive columns of ITS row.  The lane applies the epilogue in registers
+    // and writes its 128-byte row segment into a per-warp 32 x 128 B staging box in the 128B-swizzled layout
+    // (conflict-free 16-byte stores), and one lane hands the box to the TMA engine, which writes full lines to
+    // global memory and clips the M / N tails.  The saved gelu' of a backward launch arrives the same way (TMA
+    // load into the warp's other box).  No per-element address arithmetic, no LSU-side scatter: 32 lanes storing
+    // 32 different rows with ordinary vector stores were measured LSU-bound at ~2 TB/s.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    constexpr int SLICE = BN / (EW / 4);
+    constexpr int NGRP = SLICE / 64;
+    static_assert(SLICE % 64 == 0, "TMA epilogue works on 64-column groups");
+    constexpr bool kBias = (EPI & EPI_BIAS) != 0, kGelu = (EPI & EPI_GELU) != 0, kMul = (EPI & EPI_DGELU) != 0, kAux = (EPI & EPI_AUX) != 0;
+    constexpr bool kPingPong = !kAux && !kMul;          // both boxes serve the single output stream alternately
+    const EpiParams& ep = gp.ep[0];
+    const uint32_t box0 = stage_base + (uint32_t)ew * 2u * kTmaBox, box1 = box0 + kTmaBox;
+    const uint32_t my_row = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+    uint32_t aux_phase = 0;
+    int local = 0, grp_count = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
+      int m_blk, n_blk, sp, kb0, kb1;
+      gp.ts[0].decode(t, m_blk, n_blk, sp, kb0, kb1);
+      const int acc = local % NACC;
+      const uint32_t acc_phase = (local / NACC) & 1u;
+      const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's box
+      const int n_base = n_blk * BN + half * SLICE;
+      const bool live = m0 < (int)ep.M;                // a box entirely below the matrix is neither loaded nor stored
+      if (kMul && live && lane == 0) {                 // gelu' box of group 0: in flight while the MMAs of this tile still run
+        mbar_expect_tx(aux_bar(ew), kTmaBox);
+        tma_load_2d(box1, &gp.taux, aux_bar(ew), n_base, m0);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * SLICE);
+#pragma unroll 1
+      for (int g = 0; g < NGRP; ++g, ++grp_count) {
+        uint32_t z[2][32];
+        tmem_ld_32x32b_x32_issue(trow + g * 64, z[0]);
+        tmem_ld_32x32b_x32_issue(trow + g * 64 + 32, z[1]);
+        const int n0 = n_base + g * 64;
+        const uint32_t obox = kPingPong ? ((grp_count & 1) ? box1 : box0) : box0;
+        // the TMA store that last read this box must have finished reading it
+        if (lane == 0) { if (kPingPong) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        __syncwarp();
+        tmem_ld_wait(z[0]);
+        tmem_ld_wait(z[1]);
+        if (g == NGRP - 1) {                          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2 && !lead_cta) mbar_arrive_remote(tempty_bar(acc), 0);
+            else mbar_arrive(tempty_bar(acc));
+          }
+        }
+        if (!live) continue;
+        if (kMul) { mbar_wait(aux_bar(ew), aux_phase); aux_phase ^= 1u; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                 // 8 columns = one 16-byte piece of the row segment
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(z[j >> 2][(j & 3) * 8 + e]);
+          if (kBias) {
+            if (n0 + j * 8 < (int)ep.N) {             // same address in every lane: one broadcast per float4
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8 + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+          }
+          const uint32_t pos = my_row + (((uint32_t)j ^ sw) << 4);
+          float d[8];
+          if (kGelu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gelu_both(v[e], v[e], d[e]);
+          } else if (kMul) {
+            const uint4 u = lds_128(box1 + pos);
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
+          }
+          sts_128(obox + pos, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          if (kAux && kGelu) sts_128(box1 + pos, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+        }
+        fence_async_smem();                            // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();                                  // (also: every lane has consumed the gelu' box)
+        if (lane == 0) {
+          if (n0 < (int)ep.N) {
+            tma_store_2d(&gp.tc, obox, n0, m0);
+            if (kAux) tma_store_2d(&gp.taux, box1, n0, m0);
+          }
+          bulk_commit();
+          if (kMul && g + 1 < NGRP) {                  // next group's gelu' box
+            mbar_expect_tx(aux_bar(ew), kTmaBox);
+            tma_load_2d(box1, &gp.taux, aux_bar(ew), n0 + 64, m0);
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();                // the boxes must outlive the stores that read them
+    __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
     // Per 16-column chunk: TMEM -> registers (one row per lane) -> per-warp smem staging -> "4 lanes per
@@ -521,17 +687,18 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
             if (!rvalid[it]) continue;
             float4 v = *reinterpret_cast<const float4*>(stg + (it * 8 + rr) * kStagePitch + cc);
             if (has_bias) { v.x += use.bias.x; v.y += use.bias.y; v.z += use.bias.z; v.w += use.bias.w; }
-            if (F::aux(ep)) {
-              uint2 o;
-              o.x = pack_bf16x2(v.x, v.y);
-              o.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(ep.aux_out + aux_off[it] + n) = o;
-            }
+            float4 ax = v;                       // aux_out receives z, or gelu'(z) next to a GELU
             if (F::gelu(ep)) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+              gelu_both(v.x, v.x, ax.x); gelu_both(v.y, v.y, ax.y); gelu_both(v.z, v.z, ax.z); gelu_both(v.w, v.w, ax.w);
             } else if (has_auxin) {
               const float2 lo = unpack_bf16x2(use.aux[it].x), hi = unpack_bf16x2(use.aux[it].y);
-              v.x *= dgelu_erf(lo.x); v.y *= dgelu_erf(lo.y); v.z *= dgelu_erf(hi.x); v.w *= dgelu_erf(hi.y);
+              v.x *= lo.x; v.y *= lo.y; v.z *= hi.x; v.w *= hi.y;
+            }
+            if (F::aux(ep)) {
+              uint2 o;
+              o.x = pack_bf16x2(ax.x, ax.y);
+              o.y = pack_bf16x2(ax.z, ax.w);
+              *reinterpret_cast<uint2*>(ep.aux_out + aux_off[it] + n) = o;
             }
             if (has_res) { v.x += use.res[it].x; v.y += use.res[it].y; v.z += use.res[it].z; v.w += use.res[it].w; }
             if (F::red(ep)) {
@@ -643,14 +810,13 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
-template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG, int NG = 1>
-static int launch_group(const GemmGroup<NG>& gp, cudaStream_t st) {
-  // 16 epilogue warps for the GELU / dGELU epilogues of the CTA-pair kernel (one pipeline stage is traded for their staging)
-  constexpr bool kHeavy = EPI >= 0 && (EPI & (EPI_GELU | EPI_DGELU)) != 0 && CG == 2;
-  constexpr int EW = kHeavy ? 16 : 8;
-  constexpr int STAGES = kHeavy ? STAGES_ - 1 : STAGES_;
+template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG, int NG, int EW>
+static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
+  // 16 epilogue warps trade one pipeline stage for their staging (staged epilogues only)
+  constexpr int STAGES = fit_stages(STAGES_, EPI, EW, BN, CG);
+  static_assert(STAGES >= 3, "pipeline too shallow");
   constexpr int kNumThreads = 64 + 32 * EW;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EW) + kOnesBytes + 8 * (2 * STAGES + 4) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EPI, EW) + ones_bytes(EPI) + 8 * (2 * STAGES + 5 + EW) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG, EW, NG>;
@@ -677,17 +843,37 @@ static int launch_group(const GemmGroup<NG>& gp, cudaStream_t st) {
   return DAVF_OK;
 }
 
+template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG, int NG = 1>
+static int launch_group(const GemmGroup<NG>& gp, cudaStream_t st) {
+  // GELU / x gelu' epilogues of the CTA-pair kernel: 16 epilogue warps (DAVF_HEAVY_EW=8 selects 8, for experiments)
+  constexpr bool kHeavy = EPI >= 0 && (EPI & (EPI_GELU | EPI_DGELU)) != 0 && CG == 2 && !direct_epi(EPI);
+  if constexpr (kHeavy) {
+    static const int ew = [] { const char* e = getenv("DAVF_HEAVY_EW"); return e ? atoi(e) : 16; }();
+    if (ew == 16) return launch_group_ew<BN, STAGES_, AK, BKM, EPI, CG, NG, 16>(gp, st);
+  }
+  return launch_group_ew<BN, STAGES_, AK, BKM, EPI, CG, NG, 8>(gp, st);
+}
+
 template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
   GemmGroup<1> gp;
   gp.ta[0] = ta; gp.tb[0] = tb; gp.ep[0] = ep; gp.ts[0] = ts;
+  gp.tc = ta; gp.taux = ta;
+  if constexpr (direct_epi(EPI)) {
+    int rc = get_tensor_map(ep.out, ep.N, ep.M, ep.ldo, 32, &gp.tc);
+    if (rc) return rc;
+    const void* aux = (EPI & EPI_AUX) ? (const void*)ep.aux_out : (const void*)ep.aux_in;
+    if (aux) { rc = get_tensor_map(aux, ep.N, ep.M, ep.ldaux, 32, &gp.taux); if (rc) return rc; }
+  }
   gp.tile_end[0] = ts.m_tiles * ts.n_tiles * ts.splits;
   return launch_group<BN, STAGES_, AK, BKM, EPI, CG, 1>(gp, st);
 }
 
 // run-time epilogue mask of a launch, or -1 if it needs the generic kernel
+static bool direct_ok(const davf_gemm_args& a);
 static int epi_mask(const davf_gemm_args& a) {
   if (a.g > 0 || a.res_idx || a.debug_clocks) return -1;
+  if (a.out_bf16 && !a.res && !a.accumulate && !direct_ok(a)) return -1;
   int m = 0;
   if (a.rowsum_out) m |= EPI_ROWSUM;
   if (a.bias) m |= EPI_BIAS;
@@ -700,8 +886,15 @@ static int epi_mask(const davf_gemm_args& a) {
   return m;
 }
 
+// the TMA-store epilogue of the bf16-output kernels needs TMA-legal output tensors (16-byte aligned base and row pitch)
+static bool direct_ok(const davf_gemm_args& a) {
+  auto al = [](const void* p, int64_t ld) { return ((uintptr_t)p & 15) == 0 && ld % 8 == 0; };
+  return al(a.out, a.ldo) && (!a.aux_out || al(a.aux_out, a.ldaux)) && (!a.aux_in || al(a.aux_in, a.ldaux));
+}
+
 static bool has_static_epi(const davf_gemm_args& a) {
   const int em = epi_mask(a);
+  if ((em & EPI_BF16) && !direct_ok(a)) return false;
   if (a.a_kmajor && a.b_kmajor) return em == (EPI_BIAS | EPI_BF16) || em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16) || em == (EPI_BIAS | EPI_RES);
   if (a.a_kmajor && !a.b_kmajor) return em == EPI_BF16 || em == (EPI_DGELU | EPI_BF16);
   if (!a.a_kmajor && !a.b_kmajor) return em == EPI_RED || em == (EPI_RED | EPI_ROWSUM);

@@ -214,7 +214,7 @@ class MlpBranchFn(torch.autograd.Function):
         D = x.shape[-1]
         x2 = x.view(1, -1, D)
         xn, _, mean, rstd = K.layernorm_fwd(x2, None, m.norm_w.data, m.norm_b.data, m.eps)
-        a, h = linear_fwd(st, xn, m.fc1_w, m.fc1_b, act=K.ACT_GELU, want_aux=True)   # a = gelu(h), h = pre-activation
+        a, h = linear_fwd(st, xn, m.fc1_w, m.fc1_b, act=K.ACT_GELU, want_aux=True)   # a = gelu(z), h = gelu'(z) (bf16), z = fc1 output
         y = linear_fwd(st, a, m.fc2_w, m.fc2_b, res=x2.view(-1, D), out_dtype=torch.float32)
         ctx.m = m
         ctx.save_for_backward(x2, mean, rstd, xn, h, a)
@@ -228,7 +228,7 @@ class MlpBranchFn(torch.autograd.Function):
         dy = dy.contiguous()
         D = dy.shape[-1]
         dyb = K.cast_rows_bf16(dy.view(-1, D))
-        dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, act=K.ACT_DGELU, aux_in=h)      # dgrad fused with gelu'
+        dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, act=K.ACT_DGELU, aux_in=h)      # dgrad times the saved gelu'
         dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b)
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, dxn, None, dy.view(1, -1, D), None,
                                 st.grad(m.norm_w), st.grad(m.norm_b))

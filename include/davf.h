@@ -125,9 +125,12 @@ int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s);
  *     dgrad   dx = dy W  : A = dy (K-major), B = W  (MN-major, k = out-features)
  *     wgrad   dW = dy^T x: A = dy (MN-major), B = x (MN-major), k = rows
  *   z = acc + bias[n]                                   (bias may be NULL)
- *   aux_out[m*ldaux + n] = bf16(z)                      (if aux_out; pre-activation copy)
+ *   aux_out[m*ldaux + n] = bf16(act == DAVF_ACT_GELU ? gelu_erf'(z) : z)     (if aux_out)
  *   z = gelu_erf(z)                                     (if act == DAVF_ACT_GELU)
- *   z = z * gelu_erf'(aux_in[m*ldaux + n])              (if act == DAVF_ACT_DGELU; aux_in bf16)
+ *   z = z * aux_in[m*ldaux + n]                         (if act == DAVF_ACT_DGELU; aux_in bf16 = the gelu_erf'(.)
+ *                                                        the forward launch saved: the activation derivative costs
+ *                                                        two FMAs next to GELU itself, and backward -- an epilogue-
+ *                                                        bound K = 512 dgrad -- then needs no transcendental at all)
  *   row(m) = (m / g) * G + off + (m % g)                (output / residual row window; g = 0: row = m)
  *   z += res[rrow*ldres + n], rrow = res_idx ? res_idx[m] : row(m)      (if res; f32)
  *   out[row(m)*ldo + n] = z   as f32 / bf16,  or atomically += z (f32) when accumulate != 0

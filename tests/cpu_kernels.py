@@ -151,11 +151,11 @@ def gemm(a, b, a_kmajor=True, b_kmajor=True, *, bias=None, act=ACT_NONE, want_au
     M, N = z.shape
     if bias is not None:
         z = z + bias
-    aux = z.to(bf16) if want_aux else None
+    aux = (_dgelu(z) if act == ACT_GELU else z).to(bf16) if want_aux else None     # next to GELU the aux output is gelu'(z)
     if act == ACT_GELU:
         z = _gelu(z)
     elif act == ACT_DGELU:
-        z = z * _dgelu(aux_in.float().reshape(M, -1)[:, :N])
+        z = z * aux_in.float().reshape(M, -1)[:, :N]
     rows = torch.arange(M, device=z.device) if window is None else _rowmap(M, *window, z.device)
     if res is not None:
         r2 = res.reshape(-1, res.shape[-1])
