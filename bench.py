@@ -203,12 +203,19 @@ def gemm_roofline(trace, peaks, reps=5):
                 K.gemm_grouped(c)
             else:
                 K.gemm(*c[0], **c[1])
-    replay()                     # warm-up
+    replay()                     # warm-up (instantiates kernels, TMA descriptors)
+    torch.cuda.synchronize()
+    # The launch list is captured into a CUDA graph, exactly as the training step runs it: issued from Python the
+    # ~700 launches cost 10-30 us of host time each, which would time the interpreter instead of the kernels.
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        replay()
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        replay()
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 1e3 / reps

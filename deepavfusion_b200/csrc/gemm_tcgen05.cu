@@ -35,12 +35,12 @@ constexpr int UMMA_K = 16;
 constexpr int kStageCols = 16;                         // columns per epilogue chunk
 constexpr int kStagePitch = 20;                        // floats per staged row (80 B: conflict-free float4 writes)
 __host__ __device__ constexpr uint32_t staging_bytes(int epi_warps) { return epi_warps * 32 * kStagePitch * 4; }
-__host__ __device__ constexpr bool direct_epi(int epi) {   // bf16-output epilogues that store straight from registers (no staging)
-  return epi >= 0 && (epi & 32) != 0 && (epi & (16 | 64 | 128)) == 0;
+__host__ __device__ constexpr bool direct_epi(int epi) {   // compile-time epilogues: registers -> swizzled smem box -> TMA store / reduce
+  return epi >= 0;
 }
 constexpr uint32_t kTmaBox = 4096;                     // one TMA box of the direct epilogue: 32 rows x 128 B (64 bf16), SW128
 __host__ __device__ constexpr uint32_t staging_bytes(int epi, int epi_warps) { return direct_epi(epi) ? epi_warps * 2u * kTmaBox : staging_bytes(epi_warps); }
-__host__ __device__ constexpr uint32_t ones_bytes(int epi) { return direct_epi(epi) ? 0u : 2048u; }   // no row sums on the direct path
+__host__ __device__ constexpr uint32_t ones_bytes(int epi) { return (epi >= 0 && (epi & 128) == 0) ? 0u : 2048u; }   // all-ones B tile of the row-sum MMA
 // pipeline depth: what the caller asks for, capped by what fits next to the epilogue staging in 227 KB
 __host__ __device__ constexpr int fit_stages(int want, int epi, int ew, int bn, int cg) {
   const int stage = 128 * 64 * 2 + (bn / cg) * 64 * 2;
@@ -204,6 +204,11 @@ __device__ __forceinline__ void ldg_256(const void* p, uint32_t (&r)[8]) {
 // TMA store of one box from shared memory (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// f32 reduction into global memory by the TMA engine: global[box] += smem[box]
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -498,21 +503,26 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       }
     }
   } else if constexpr (direct_epi(EPI)) {
-    // ===================== TMA-store epilogue (bf16 outputs: bias / GELU / x gelu') =====================
-    // tcgen05.ld hands every lane 64 consecutive columns of ITS row.  The lane applies the epilogue in registers
-    // and writes its 128-byte row segment into a per-warp 32 x 128 B staging box in the 128B-swizzled layout
-    // (conflict-free 16-byte stores), and one lane hands the box to the TMA engine, which writes full lines to
-    // global memory and clips the M / N tails.  The saved gelu' of a backward launch arrives the same way (TMA
-    // load into the warp's other box).  No per-element address arithmetic, no LSU-side scatter: 32 lanes storing
-    // 32 different rows with ordinary vector stores were measured LSU-bound at ~2 TB/s.
+    // ===================== TMA epilogue (every compile-time epilogue) =====================
+    // tcgen05.ld hands every lane consecutive columns of ITS row.  The lane applies the epilogue in registers and
+    // writes its 128-byte row segment (64 bf16 or 32 f32 columns) into a per-warp 32 x 128 B box in the
+    // 128B-swizzled layout (conflict-free 16-byte stores); one lane hands the box to the TMA engine, which writes
+    // (or, for wgrad, f32-ADDS: cp.reduce.async.bulk) full lines to global memory and clips the M / N tails.
+    // Operands of the epilogue that are matrices (the saved gelu' of a backward launch, the f32 residual) arrive
+    // the same way, by a TMA load into the warp's second box.  No per-element address arithmetic and no LSU-side
+    // scatter: 32 lanes storing 32 different rows with ordinary vector stores were measured LSU-bound at ~2 TB/s.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int ew = warp - 2;
     constexpr int SLICE = BN / (EW / 4);
-    constexpr int NGRP = SLICE / 64;
-    static_assert(SLICE % 64 == 0, "TMA epilogue works on 64-column groups");
     constexpr bool kBias = (EPI & EPI_BIAS) != 0, kGelu = (EPI & EPI_GELU) != 0, kMul = (EPI & EPI_DGELU) != 0, kAux = (EPI & EPI_AUX) != 0;
-    constexpr bool kPingPong = !kAux && !kMul;          // both boxes serve the single output stream alternately
+    constexpr bool kRes = (EPI & EPI_RES) != 0, kRed = (EPI & EPI_RED) != 0, kRowsum = (EPI & EPI_ROWSUM) != 0, kF32 = (EPI & EPI_BF16) == 0;
+    static_assert(!(kF32 && (kGelu || kMul || kAux)) && !(kRes && !kF32) && !(kRed && !kF32), "unsupported compile-time epilogue");
+    constexpr int GW = kF32 ? 32 : 64;                  // columns per box (128 bytes per row)
+    constexpr int NGRP = SLICE / GW;
+    static_assert(SLICE % GW == 0, "TMA epilogue works on whole boxes");
+    constexpr bool kLoad = kMul || kRes;                // box1 receives a TMA load
+    constexpr bool kPingPong = !kAux && !kLoad;         // both boxes serve the single output stream alternately
     const EpiParams& ep = gp.ep[0];
     const uint32_t box0 = stage_base + (uint32_t)ew * 2u * kTmaBox, box1 = box0 + kTmaBox;
     const uint32_t my_row = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
@@ -523,28 +533,33 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       gp.ts[0].decode(t, m_blk, n_blk, sp, kb0, kb1);
       const int acc = local % NACC;
       const uint32_t acc_phase = (local / NACC) & 1u;
-      const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's box
+      const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's boxes
       const int n_base = n_blk * BN + half * SLICE;
       const bool live = m0 < (int)ep.M;                // a box entirely below the matrix is neither loaded nor stored
-      if (kMul && live && lane == 0) {                 // gelu' box of group 0: in flight while the MMAs of this tile still run
+      const bool add_bias = kBias && sp == 0;
+      if (kLoad && live && lane == 0 && n_base < (int)ep.N) {     // operand box of group 0: in flight while the MMAs of this tile still run
         mbar_expect_tx(aux_bar(ew), kTmaBox);
         tma_load_2d(box1, &gp.taux, aux_bar(ew), n_base, m0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (kRowsum && n_blk == 0 && half == 0) {
+        const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
+        if (m0 + lane < (int)ep.M) atomicAdd(ep.rowsum_out + m0 + lane, rs);
+      }
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * SLICE);
 #pragma unroll 1
       for (int g = 0; g < NGRP; ++g, ++grp_count) {
-        uint32_t z[2][32];
-        tmem_ld_32x32b_x32_issue(trow + g * 64, z[0]);
-        tmem_ld_32x32b_x32_issue(trow + g * 64 + 32, z[1]);
-        const int n0 = n_base + g * 64;
+        uint32_t z[GW / 32][32];
+#pragma unroll
+        for (int h = 0; h < GW / 32; ++h) tmem_ld_32x32b_x32_issue(trow + g * GW + h * 32, z[h]);
+        const int n0 = n_base + g * GW;
         const uint32_t obox = kPingPong ? ((grp_count & 1) ? box1 : box0) : box0;
         // the TMA store that last read this box must have finished reading it
         if (lane == 0) { if (kPingPong) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
         __syncwarp();
-        tmem_ld_wait(z[0]);
-        tmem_ld_wait(z[1]);
+#pragma unroll
+        for (int h = 0; h < GW / 32; ++h) tmem_ld_wait(z[h]);
         if (g == NGRP - 1) {                          // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -553,44 +568,59 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
             else mbar_arrive(tempty_bar(acc));
           }
         }
-        if (!live) continue;
-        if (kMul) { mbar_wait(aux_bar(ew), aux_phase); aux_phase ^= 1u; }
+        const bool active = live && n0 < (int)ep.N;   // warp-uniform
+        if (active) {
+          if (kLoad) { mbar_wait(aux_bar(ew), aux_phase); aux_phase ^= 1u; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                 // 8 columns = one 16-byte piece of the row segment
-          float v[8];
+          for (int j = 0; j < 8; ++j) {               // one 16-byte piece of the row segment: 8 bf16 or 4 f32 columns
+            const uint32_t pos = my_row + (((uint32_t)j ^ sw) << 4);
+            if constexpr (kF32) {
+              float v[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(z[j >> 2][(j & 3) * 8 + e]);
-          if (kBias) {
-            if (n0 + j * 8 < (int)ep.N) {             // same address in every lane: one broadcast per float4
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8 + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(z[0][j * 4 + e]);
+              if (add_bias && n0 + j * 4 < (int)ep.N) {   // same address in every lane: one broadcast
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 4));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (kRes) {
+                const uint4 u = lds_128(box1 + pos);
+                v[0] += __uint_as_float(u.x); v[1] += __uint_as_float(u.y); v[2] += __uint_as_float(u.z); v[3] += __uint_as_float(u.w);
+              }
+              sts_128(obox + pos, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+            } else {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(z[j >> 2][(j & 3) * 8 + e]);
+              if (add_bias && n0 + j * 8 < (int)ep.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 8 + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              float d[8];
+              if (kGelu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gelu_both(v[e], v[e], d[e]);
+              } else if (kMul) {
+                const uint4 u = lds_128(box1 + pos);
+                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
+              }
+              sts_128(obox + pos, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              if (kAux && kGelu) sts_128(box1 + pos, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
             }
           }
-          const uint32_t pos = my_row + (((uint32_t)j ^ sw) << 4);
-          float d[8];
-          if (kGelu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) gelu_both(v[e], v[e], d[e]);
-          } else if (kMul) {
-            const uint4 u = lds_128(box1 + pos);
-            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-            v[0] *= a0.x; v[1] *= a0.y; v[2] *= a1.x; v[3] *= a1.y; v[4] *= a2.x; v[5] *= a2.y; v[6] *= a3.x; v[7] *= a3.y;
-          }
-          sts_128(obox + pos, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          if (kAux && kGelu) sts_128(box1 + pos, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+          fence_async_smem();                          // generic-proxy writes -> visible to the TMA engine
         }
-        fence_async_smem();                            // generic-proxy writes -> visible to the TMA engine
-        __syncwarp();                                  // (also: every lane has consumed the gelu' box)
+        __syncwarp();                                  // (also: every lane has consumed the operand box)
         if (lane == 0) {
-          if (n0 < (int)ep.N) {
-            tma_store_2d(&gp.tc, obox, n0, m0);
+          if (active) {
+            if (kRed) tma_reduce_add_2d(&gp.tc, obox, n0, m0); else tma_store_2d(&gp.tc, obox, n0, m0);
             if (kAux) tma_store_2d(&gp.taux, box1, n0, m0);
           }
           bulk_commit();
-          if (kMul && g + 1 < NGRP) {                  // next group's gelu' box
+          if (kLoad && live && g + 1 < NGRP && n0 + GW < (int)ep.N) {     // next group's operand box
             mbar_expect_tx(aux_bar(ew), kTmaBox);
-            tma_load_2d(box1, &gp.taux, aux_bar(ew), n0 + 64, m0);
+            tma_load_2d(box1, &gp.taux, aux_bar(ew), n0 + GW, m0);
           }
         }
       }
@@ -759,7 +789,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int64_t inner, outer, ld; int box_outer;
+  const void* ptr; int64_t inner, outer, ld; int box_outer;     // box_outer < 0: f32 tensor, box {32, -box_outer}
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
   }
@@ -788,12 +818,13 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   }
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DAVF_ECUDA; }
+  const bool f32 = box_outer < 0;                  // f32 epilogue tensors: 32 columns = 128 bytes per box row
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)(f32 ? -box_outer : box_outer)};
   cuuint32_t estr[2] = {1u, 1u};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -859,11 +890,17 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
   GemmGroup<1> gp;
   gp.ta[0] = ta; gp.tb[0] = tb; gp.ep[0] = ep; gp.ts[0] = ts;
   gp.tc = ta; gp.taux = ta;
-  if constexpr (direct_epi(EPI)) {
-    int rc = get_tensor_map(ep.out, ep.N, ep.M, ep.ldo, 32, &gp.tc);
+  if constexpr (direct_epi(EPI)) {           // epilogue tensors as [M][N] TMA tensors, box = 32 rows x 128 bytes
+    constexpr bool kF32 = (EPI & EPI_BF16) == 0;
+    int rc = get_tensor_map(ep.out, ep.N, ep.M, ep.ldo, kF32 ? -32 : 32, &gp.tc);
     if (rc) return rc;
-    const void* aux = (EPI & EPI_AUX) ? (const void*)ep.aux_out : (const void*)ep.aux_in;
-    if (aux) { rc = get_tensor_map(aux, ep.N, ep.M, ep.ldaux, 32, &gp.taux); if (rc) return rc; }
+    if constexpr ((EPI & EPI_RES) != 0) {
+      rc = get_tensor_map(ep.res, ep.N, ep.M, ep.ldres, -32, &gp.taux);
+    } else if constexpr ((EPI & (EPI_AUX | EPI_DGELU)) != 0) {
+      const void* aux = (EPI & EPI_AUX) ? (const void*)ep.aux_out : (const void*)ep.aux_in;
+      rc = get_tensor_map(aux, ep.N, ep.M, ep.ldaux, 32, &gp.taux);
+    }
+    if (rc) return rc;
   }
   gp.tile_end[0] = ts.m_tiles * ts.n_tiles * ts.splits;
   return launch_group<BN, STAGES_, AK, BKM, EPI, CG, 1>(gp, st);
@@ -873,7 +910,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
 static bool direct_ok(const davf_gemm_args& a);
 static int epi_mask(const davf_gemm_args& a) {
   if (a.g > 0 || a.res_idx || a.debug_clocks) return -1;
-  if (a.out_bf16 && !a.res && !a.accumulate && !direct_ok(a)) return -1;
+  if (!direct_ok(a)) return -1;
   int m = 0;
   if (a.rowsum_out) m |= EPI_ROWSUM;
   if (a.bias) m |= EPI_BIAS;
@@ -888,13 +925,14 @@ static int epi_mask(const davf_gemm_args& a) {
 
 // the TMA-store epilogue of the bf16-output kernels needs TMA-legal output tensors (16-byte aligned base and row pitch)
 static bool direct_ok(const davf_gemm_args& a) {
-  auto al = [](const void* p, int64_t ld) { return ((uintptr_t)p & 15) == 0 && ld % 8 == 0; };
-  return al(a.out, a.ldo) && (!a.aux_out || al(a.aux_out, a.ldaux)) && (!a.aux_in || al(a.aux_in, a.ldaux));
+  auto al = [](const void* p, int64_t ld, int esz) { return ((uintptr_t)p & 15) == 0 && (ld * esz) % 16 == 0; };
+  return al(a.out, a.ldo, a.out_bf16 ? 2 : 4) && (!a.aux_out || al(a.aux_out, a.ldaux, 2)) && (!a.aux_in || al(a.aux_in, a.ldaux, 2)) &&
+         (!a.res || al(a.res, a.ldres, 4));
 }
 
 static bool has_static_epi(const davf_gemm_args& a) {
   const int em = epi_mask(a);
-  if ((em & EPI_BF16) && !direct_ok(a)) return false;
+  if (em < 0) return false;
   if (a.a_kmajor && a.b_kmajor) return em == (EPI_BIAS | EPI_BF16) || em == (EPI_BIAS | EPI_GELU | EPI_AUX | EPI_BF16) || em == (EPI_BIAS | EPI_RES);
   if (a.a_kmajor && !a.b_kmajor) return em == EPI_BF16 || em == (EPI_DGELU | EPI_BF16);
   if (!a.a_kmajor && !a.b_kmajor) return em == EPI_RED || em == (EPI_RED | EPI_ROWSUM);

@@ -76,18 +76,23 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(davf_ln_fwd_args a, RowMap 
   }
 }
 
+// Two CTAs (16 warps) per SM: the kernel is a pure stream (14-18 bytes per element), so what matters is bytes in
+// flight per SM.  gamma is re-read through L1 per row instead of living in 4 VEC registers.
 template <int VEC>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap rm, int64_t rows) {
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(davf_ln_bwd_args a, RowMap rm, int64_t rows) {
   extern __shared__ __align__(16) float sm_red[];   // [warps][2*D] : per-warp dgamma | dbeta partials
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)a.D;
-  float4 gam[VEC], dg[VEC], db[VEC];
+  const float4* gam = reinterpret_cast<const float4*>(a.gamma) + lane;     // gam[i * 32] = gamma of this lane's i-th float4
+  // dgamma / dbeta partials of this warp live in its private slice of shared memory (every lane only ever touches
+  // its own columns: no atomics, no syncs) instead of 8 VEC registers
+  float4* my_dg = reinterpret_cast<float4*>(sm_red + (size_t)(threadIdx.x >> 5) * 2 * a.D) + lane;
+  float4* my_db = my_dg + a.D / 4;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    gam[i] = *reinterpret_cast<const float4*>(a.gamma + (i * 32 + lane) * 4);
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = dg[i];
+    my_dg[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    my_db[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t R = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); R < rows; R += (int64_t)gridDim.x * wpb) {
     const int b = (int)(R / rm.n), r = (int)(R - (int64_t)b * rm.n);
@@ -114,9 +119,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap 
         d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
       }
       dy[i] = d;
-      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-      const float g0 = d.x * gam[i].x, g1 = d.y * gam[i].y, g2 = d.z * gam[i].z, g3 = d.w * gam[i].w;
+      float4 sb = my_db[i * 32], sg = my_dg[i * 32];
+      sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
+      sg.x += d.x * xh[i].x; sg.y += d.y * xh[i].y; sg.z += d.z * xh[i].z; sg.w += d.w * xh[i].w;
+      my_db[i * 32] = sb; my_dg[i * 32] = sg;
+      const float4 gm = __ldg(gam + i * 32);
+      const float g0 = d.x * gm.x, g1 = d.y * gm.y, g2 = d.z * gm.z, g3 = d.w * gm.w;
       s1 += (g0 + g1) + (g2 + g3);
       s2 += (g0 * xh[i].x + g1 * xh[i].y) + (g2 * xh[i].z + g3 * xh[i].w);
     }
@@ -129,11 +137,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap 
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int col = (i * 32 + lane) * 4;
+        const float4 gm = __ldg(gam + i * 32);
         float4 o;
-        o.x = rstd * (dy[i].x * gam[i].x - c1 - xh[i].x * c2);
-        o.y = rstd * (dy[i].y * gam[i].y - c1 - xh[i].y * c2);
-        o.z = rstd * (dy[i].z * gam[i].z - c1 - xh[i].z * c2);
-        o.w = rstd * (dy[i].w * gam[i].w - c1 - xh[i].w * c2);
+        o.x = rstd * (dy[i].x * gm.x - c1 - xh[i].x * c2);
+        o.y = rstd * (dy[i].y * gm.y - c1 - xh[i].y * c2);
+        o.z = rstd * (dy[i].z * gm.z - c1 - xh[i].z * c2);
+        o.w = rstd * (dy[i].w * gm.w - c1 - xh[i].w * c2);
         if (add) {
           const float4 r4 = *reinterpret_cast<const float4*>(add + col);
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
@@ -144,14 +153,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(davf_ln_bwd_args a, RowMap 
   }
   // CTA-level reduction of dgamma / dbeta: every warp stores its partials (plain stores, no shared atomics),
   // 4 columns per thread are summed over the warps, then ONE vector f32 reduction per 4 columns goes to HBM.
-  const int warp = threadIdx.x >> 5;
-  float* my = sm_red + (size_t)warp * 2 * a.D;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    *reinterpret_cast<float4*>(my + col) = dg[i];
-    *reinterpret_cast<float4*>(my + a.D + col) = db[i];
-  }
   __syncthreads();
   const int ncol4 = 2 * a.D / 4;
   for (int i = threadIdx.x; i < ncol4; i += blockDim.x) {
@@ -230,6 +231,10 @@ extern "C" int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s) {
     DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    // two 48 KB CTAs per SM: ask for the large shared-memory carve-out explicitly
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    DAVF_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   switch (a->D / 128) {
