@@ -36,7 +36,8 @@ class LnBwdArgs(C.Structure):
                 ("dx0", vp), ("dbs0", C.c_int64), ("add0", vp),
                 ("dx1", vp), ("dbs1", C.c_int64), ("add1", vp),
                 ("dgamma", vp), ("dbeta", vp),
-                ("nseg", C.c_int), ("seg_start", C.c_int * 5)]
+                ("nseg", C.c_int), ("seg_start", C.c_int * 5),
+                ("dx0_bf16", vp), ("dx1_bf16", vp)]
 
 
 class GemmArgs(C.Structure):

@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(davf_ln_bwd_args a, RowM
                        : (a.dx1 ? a.dx1 + (int64_t)b * a.dbs1 + (int64_t)(r - rm.n0) * a.D : nullptr);
     const float* add = first ? (a.add0 ? a.add0 + (int64_t)b * a.dbs0 + (int64_t)r * a.D : nullptr)
                              : (a.add1 ? a.add1 + (int64_t)b * a.dbs1 + (int64_t)(r - rm.n0) * a.D : nullptr);
+    uint16_t* dst_lp = first ? (a.dx0_bf16 ? a.dx0_bf16 + ((int64_t)b * rm.n0 + r) * a.D : nullptr)
+                             : (a.dx1_bf16 ? a.dx1_bf16 + ((int64_t)b * rm.n1 + (r - rm.n0)) * a.D : nullptr);
     if (dst) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -148,6 +150,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(davf_ln_bwd_args a, RowM
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
         }
         *reinterpret_cast<float4*>(dst + col) = o;
+        if (dst_lp) {
+          uint2 u;
+          u.x = pack_bf16x2(o.x, o.y);
+          u.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dst_lp + col) = u;
+        }
       }
     }
   }

@@ -66,6 +66,16 @@ def _f32_rows(t: Tensor) -> Tensor:
     return t.reshape(-1, t.shape[-1])
 
 
+def _lowp_grad(st: ParamStore, dy2d: Tensor) -> Tensor:
+    """bf16 copy of an incoming f32 gradient [rows, D]: the one its producer already wrote, else a cast launch."""
+    lp = st.take_lowp_grad(dy2d)
+    return lp.view(dy2d.shape) if lp is not None else K.cast_rows_bf16(dy2d)
+
+
+def _new_lowp(like: Tensor) -> Tensor:
+    return torch.empty(like.numel() // like.shape[-1], like.shape[-1], dtype=torch.bfloat16, device=like.device)
+
+
 def params_of(ns: SimpleNamespace):
     """All nn.Parameters referenced by a region namespace (nested namespaces included)."""
     out = []
@@ -110,7 +120,7 @@ class PatchEmbedFn(torch.autograd.Function):
     def backward(ctx, dx: Tensor):
         m = ctx.m
         (a,) = ctx.saved_tensors
-        dxb = K.cast_rows_bf16(_f32_rows(dx.contiguous()))
+        dxb = _lowp_grad(m.store, _f32_rows(dx.contiguous()))
         linear_bwd(m.store, dxb, a, m.weight, m.bias, need_dx=False)
         _done(m)
         return None, None, None, None
@@ -182,7 +192,7 @@ class AttnBranchFn(torch.autograd.Function):
         B, n, D = dy.shape
         S, H = nP + n, m.heads
         hd = D // H
-        dyb = K.cast_rows_bf16(dy.view(B * n, D))
+        dyb = _lowp_grad(st, dy.view(B * n, D))
         do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b)                # [B*n, D] bf16
         dqkv = torch.empty_like(qkv)
         d5 = dqkv.view(B, S, 3, H, hd)
@@ -196,8 +206,10 @@ class AttnBranchFn(torch.autograd.Function):
         if nP:
             dxp, dx = K.layernorm_bwd(x0, x1, m.norm_w.data, mean, rstd, dxn, None, None, dy, gw, gb,
                                       need_dx0=ctx.needs_input_grad[0])
-        else:
-            dx, _ = K.layernorm_bwd(x0, None, m.norm_w.data, mean, rstd, dxn, None, dy, None, gw, gb)
+        else:       # single consumer upstream (the previous block's MLP branch): hand it the bf16 copy too
+            lp = _new_lowp(dy)
+            dx, _ = K.layernorm_bwd(x0, None, m.norm_w.data, mean, rstd, dxn, None, dy, None, gw, gb, dx0_lowp=lp)
+            st.stash_lowp_grad(dx, lp)
             dxp = None
         _done(m)
         return dxp, dx, None, None
@@ -227,13 +239,16 @@ class MlpBranchFn(torch.autograd.Function):
         x2, mean, rstd, xn, h, a = ctx.saved_tensors
         dy = dy.contiguous()
         D = dy.shape[-1]
-        dyb = K.cast_rows_bf16(dy.view(-1, D))
+        dyb = _lowp_grad(st, dy.view(-1, D))
         dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, act=K.ACT_DGELU, aux_in=h)      # dgrad times the saved gelu'
         dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b)
+        lp = _new_lowp(dy)                                                            # consumed by the attention branch's backward
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, dxn, None, dy.view(1, -1, D), None,
-                                st.grad(m.norm_w), st.grad(m.norm_b))
+                                st.grad(m.norm_w), st.grad(m.norm_b), dx0_lowp=lp)
+        dx = dx.view(dy.shape)
+        st.stash_lowp_grad(dx, lp)
         _done(m)
-        return dx.view(dy.shape), None, None
+        return dx, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -256,10 +271,13 @@ class LayerNormFn(torch.autograd.Function):
         st: ParamStore = m.store
         x2, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
+        lp = _new_lowp(dy)
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, None, dy.view(-1, dy.shape[-1]), None, None,
-                                st.grad(m.norm_w), st.grad(m.norm_b))
+                                st.grad(m.norm_w), st.grad(m.norm_b), dx0_lowp=lp)
+        dx = dx.view(dy.shape)
+        st.stash_lowp_grad(dx, lp)
         _done(m)
-        return dx.view(dy.shape), None, None
+        return dx, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -448,9 +466,9 @@ class FusionAttnFn(torch.autograd.Function):
         kvv5, dkvv5 = kvv.view(B, Nv, 2, H, hd), dkvv.view(B, Nv, 2, H, hd)
         kva5, dkva5 = kva.view(B, Na, 2, H, hd), dkva.view(B, Na, 2, H, hd)
         K.attention_bwd(qv.view(B, nv, H, hd), kvv5[:, :, 0], kvv5[:, :, 1], do_v.view(B, nv, H, hd), lse_v, scale,
-                        dqv.view(B, nv, H, hd), dkvv5[:, :, 0], dkvv5[:, :, 1])
+                        dqv.view(B, nv, H, hd), dkvv5[:, :, 0], dkvv5[:, :, 1], o=ov.view(B, nv, H, hd))
         K.attention_bwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], do_a.view(B, na, H, hd), lse_a, scale,
-                        dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1])
+                        dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1], o=oa.view(B, na, H, hd))
         _, _, dxv_n, dxa_n = group_bwd(st, [(dqv, mv, L.q_v, dict(out=dmv)), (dqa, ma, L.q_a, dict(out=dma)),
                                             (dkvv, xv_n, L.kv_v, {}), (dkva, xa_n, L.kv_a, {})])
 

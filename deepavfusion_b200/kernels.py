@@ -149,9 +149,11 @@ def layernorm_bwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor,
                   dy_bf16: Optional[Tensor], dy_f32: Optional[Tensor],
                   add0: Optional[Tensor], add1: Optional[Tensor], dgamma: Tensor, dbeta: Tensor,
                   seg_start: Optional[Sequence[int]] = None, need_dx0: bool = True, need_dx1: bool = True,
-                  dx0_out: Optional[Tensor] = None):
+                  dx0_out: Optional[Tensor] = None, dx0_lowp: Optional[Tensor] = None, dx1_lowp: Optional[Tensor] = None):
     """Returns (dx0 [B,n0,D] f32, dx1 [B,n1,D] f32 or None); dgamma / dbeta are accumulated in place.
-    ``dx0_out`` may be a [B,n0,D] view with a batch stride (rows dense) to write dx0 in place."""
+    ``dx0_out`` may be a [B,n0,D] view with a batch stride (rows dense) to write dx0 in place.
+    ``dx0_lowp`` / ``dx1_lowp``: optional contiguous bf16 [B*n0, D] / [B*n1, D] tensors that receive a bf16 copy of
+    the dx rows (the GEMM operand of the next backward region)."""
     B, n0, D = x0.shape
     n1 = x1.shape[1] if x1 is not None else 0
     dev = x0.device
@@ -175,6 +177,12 @@ def layernorm_bwd(x0: Tensor, x1: Optional[Tensor], gamma: Tensor, mean: Tensor,
     a.add1 = _need(add1, torch.float32, "add1").data_ptr() if add1 is not None else 0
     a.dgamma, a.dbeta = _need(dgamma, torch.float32, "dgamma").data_ptr(), _need(dbeta, torch.float32, "dbeta").data_ptr()
     a.nseg = _segs(a.seg_start, seg_start)
+    if dx0_lowp is not None:
+        assert dx0 is not None and dx0_lowp.numel() == B * n0 * D
+        a.dx0_bf16 = _need(dx0_lowp, torch.bfloat16, "dx0_lowp").data_ptr()
+    if dx1_lowp is not None:
+        assert dx1 is not None and dx1_lowp.numel() == B * n1 * D
+        a.dx1_bf16 = _need(dx1_lowp, torch.bfloat16, "dx1_lowp").data_ptr()
     check(_cabi.lib().davf_layernorm_bwd(C.byref(a), _stream()), "davf_layernorm_bwd")
     return dx0, dx1
 

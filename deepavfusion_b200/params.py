@@ -117,10 +117,13 @@ class ParamStore:
         self.side_streams = []    # streams the model issues independent branches on (see DeepAVFusion._side_streams)
         self.main_stream = None   # the stream the current forward was issued on
         self._join_pending = False
+        self._lowp_grads = {}     # data_ptr of an f32 activation gradient -> (tensor, version, bf16 copy); see stash_lowp_grad
         self.refresh_lowp(force=True)
 
     # -- re-entrancy: nested module forwards skip the per-forward checks ------------------------
     def __enter__(self):
+        if self._depth == 0:
+            self._lowp_grads.clear()
         self._depth += 1
         return self
 
@@ -183,6 +186,19 @@ class ParamStore:
             self.ensure_grads(force=True)
         return self.flat_lp[o1:o1 + n].view(shape), self.flat_g[o1:o1 + n].view(shape)
 
+    # -- bf16 copies of activation gradients ------------------------------------------------------
+    def stash_lowp_grad(self, g: torch.Tensor, lp: torch.Tensor) -> None:
+        """The kernel that produced the f32 gradient ``g`` (LayerNorm backward) also wrote its bf16 copy ``lp``; the
+        next backward region, which needs ``g`` as a bf16 GEMM operand, picks it up with ``take_lowp_grad`` instead
+        of launching a cast.  The entry pins ``g``, so a later tensor with the same address is the same tensor."""
+        self._lowp_grads[g.data_ptr()] = (g, g._version, lp)
+
+    def take_lowp_grad(self, g: torch.Tensor):
+        e = self._lowp_grads.pop(g.data_ptr(), None)
+        if e is None or e[0].numel() != g.numel() or e[0]._version != e[1] or g.dtype != torch.float32:
+            return None
+        return e[2]
+
     # -- gradients ------------------------------------------------------------------------------
     def _attached(self, p: nn.Parameter, k: int) -> bool:
         g = p.grad
@@ -241,6 +257,7 @@ class ParamStore:
 
         def join():
             self._join_pending = False
+            self._lowp_grads.clear()
             self.join_side_streams(self.main_stream)
         torch.autograd.Variable._execution_engine.queue_callback(join)
 

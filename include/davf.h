@@ -110,6 +110,9 @@ typedef struct {
   float* dx1; int64_t dbs1; const float* add1;
   float* dgamma; float* dbeta;
   int nseg; int seg_start[5];
+  /* optional bf16 copies of the dx0 / dx1 rows, compact [B*n0, D] / [B*n1, D]: the next backward region consumes the
+   * gradient as a bf16 GEMM operand, so the f32 -> bf16 pass over it is folded into this kernel */
+  davf_bf16* dx0_bf16; davf_bf16* dx1_bf16;
 } davf_ln_bwd_args;
 int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s);
 

@@ -95,7 +95,7 @@ def layernorm_fwd(x0, x1, gamma, beta, eps, want_bf16=True, want_f32=False, seg_
 
 
 def layernorm_bwd(x0, x1, gamma, mean, rstd, dy_bf16, dy_f32, add0, add1, dgamma, dbeta, seg_start=None,
-                  need_dx0=True, need_dx1=True, dx0_out=None):
+                  need_dx0=True, need_dx1=True, dx0_out=None, dx0_lowp=None, dx1_lowp=None):
     x = x0 if x1 is None else torch.cat([x0, x1], dim=1)
     B, n, D = x.shape
     n0 = x0.shape[1]
@@ -125,6 +125,10 @@ def layernorm_bwd(x0, x1, gamma, mean, rstd, dy_bf16, dy_f32, add0, add1, dgamma
         if add1 is not None:
             dx1 = dx1 + add1.reshape(B, n - n0, D)
         dx1 = dx1.contiguous() if need_dx1 else None
+    if dx0_lowp is not None:
+        dx0_lowp.copy_(dx0.reshape(dx0_lowp.shape))
+    if dx1_lowp is not None:
+        dx1_lowp.copy_(dx1.reshape(dx1_lowp.shape))
     if dx0_out is not None:
         dx0_out.copy_(dx0)
         dx0 = dx0_out
