@@ -208,7 +208,7 @@ def gemm_roofline(trace, peaks, reps=5):
     # The launch list is captured into a CUDA graph, exactly as the training step runs it: issued from Python the
     # ~700 launches cost 10-30 us of host time each, which would time the interpreter instead of the kernels.
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):     # (an NCCL watchdog thread may be alive in this process)
         replay()
     graph.replay()
     torch.cuda.synchronize()
@@ -348,7 +348,8 @@ def run_ours(args):
                     config=dict(workload=WORKLOAD, global_batch=BATCH_PER_GPU * world, parallelism=f"dp{world}",
                                 step="mask + fwd + bwd + grad all-reduce + fused AdamW", cuda_graph=bool(use_graph),
                                 streams=os.environ.get("DAVF_STREAMS", "1") != "0",
-                                allreduce=("none" if world == 1 else ("one NCCL call after the captured fwd+bwd graph" if use_graph else "bucketed, overlapped with backward")),
+                                allreduce=("none" if world == 1 else (("bucketed NCCL all-reduce captured inside the step graph, overlapped with backward" if getattr(step, "overlap_comm", False)
+                                                                      else "one NCCL call after the captured fwd+bwd graph") if use_graph else "bucketed, overlapped with backward")),
                                 l2="per-step working set (640 MB bf16 weights + >4 GB activations) exceeds the 126 MB L2; no flush needed",
                                 gflop_per_pair=GFLOP_PER_PAIR, step_tflops=step_tflops, step_frac_of_peak=step_tflops / (peaks["tflops"] * world)),
                     e2e=dict(value=e2e_value, unit="clip-pairs/s", h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=4 * world,
@@ -359,8 +360,11 @@ def run_ours(args):
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # No NCCL teardown: destroying the process group while a captured graph still holds NCCL kernel nodes hung at
+        # exit on this stack.  Every rank has synchronised its device; leave without running destructors.
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -4,11 +4,16 @@ replayed, removing the ~2,000 per-step launches' CPU cost and every host sync fr
 beta^t, grad scale) live in device tables the captured kernels read, so LR schedules need no
 re-capture; the mask noise comes from torch's graph-safe Philox generator state.
 
-Data-parallel runs capture forward + backward only; the gradient all-reduce (one NCCL call over the flat
-f32 gradient buffer) and the fused AdamW launch follow the replay on the same stream.  (Capturing the
-bucketed, backward-overlapped NCCL calls inside the graph hung on this software stack; the eager
-``Trainer`` path keeps the overlap.)"""
+Data-parallel runs capture the bucketed gradient all-reduce too (``overlap_comm``, the default): every bucket's
+NCCL call is recorded on the communication stream at the point of backward where its last gradient has been
+produced, so in the replayed graph the all-reduce of the decoder / late-encoder buckets runs under the rest of
+backward, and the fused AdamW node follows the last bucket.  NCCL needs its communicator and internal stream
+to exist before capture: the eager warm-up steps run the identical bucketed path.  ``DAVF_GRAPH_NCCL=0`` (or
+``overlap_comm=False``) falls back to capturing forward + backward only, with one all-reduce over the flat
+gradient buffer and the AdamW launch issued after the replay."""
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -19,9 +24,11 @@ class GraphedTrainStep:
     freeing such a tensor while a capture is in progress invalidates the capture."""
 
     def __init__(self, trainer, image_example: torch.Tensor, audio_example: torch.Tensor, warmup: int = 3,
-                 capture_error_mode: str = "thread_local"):
+                 capture_error_mode: str = "thread_local", overlap_comm: bool = True):
         assert trainer.accum_iter == 1, "graph capture covers one full optimizer step (accum_iter == 1)"
         self.trainer = trainer
+        self.distributed = trainer.sync is not None
+        self.overlap_comm = self.distributed and overlap_comm and os.environ.get("DAVF_GRAPH_NCCL", "1") != "0"
         self.image = torch.empty_like(image_example)
         self.audio = torch.empty_like(audio_example)
         self.image.copy_(image_example)
@@ -37,17 +44,16 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         opt._sync_hp()
         self.graph = torch.cuda.CUDAGraph()
-        self.distributed = trainer.sync is not None
         from .. import kernels as K
         n0 = K.launch_count()
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss_image, self.loss_audio, self.grad_norm = self._one_step(sync_hp=False, capturing=True)
-        self.launches_per_step = K.launch_count() - n0 + (1 if self.distributed else 0)
+        self.launches_per_step = K.launch_count() - n0 + (1 if (self.distributed and not self.overlap_comm) else 0)
 
     def _one_step(self, sync_hp: bool = True, capturing: bool = False):
         tr = self.trainer
         li, la, _, _ = tr.model(self.image, self.audio)
-        if self.__dict__.get("distributed", tr.sync is not None):
+        if self.distributed and not self.overlap_comm:
             tr.sync.enabled = False                      # no NCCL inside the captured region
             (li + la).backward()
             tr.store.join_side_streams(torch.cuda.current_stream())
@@ -72,7 +78,7 @@ class GraphedTrainStep:
         self.audio.copy_(audio, non_blocking=True)
         self.trainer.optimizer._sync_hp()
         self.graph.replay()
-        if self.distributed:
+        if self.distributed and not self.overlap_comm:
             self._reduce_and_step(sync_hp=False)
             self.grad_norm = self.trainer.optimizer.grad_norm()
         else:
