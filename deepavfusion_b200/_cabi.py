@@ -106,6 +106,12 @@ SIGNATURES = {
     "davf_adamw_step": (i, [vp, vp, vp, vp, vp, i64, vp, vp, vp, f, f, f, i, vp, vp]),
     "davf_sumsq_f32": (i, [vp, i64, vp, vp]),
     "davf_cast_flat_bf16": (i, [vp, vp, i64, vp]),
+    "davf_meanpool_fwd": (i, [vp, i64, i, i, i, vp, vp]),
+    "davf_meanpool_bwd": (i, [vp, i, i, i, vp, vp]),
+    "davf_batchnorm1d_fwd": (i, [vp, i, i, i, vp, vp, f, f, vp, vp, vp, vp]),
+    "davf_batchnorm1d_bwd": (i, [vp, vp, vp, vp, i, i, i, vp, vp]),
+    "davf_head_fwd": (i, [vp, vp, vp, i, i, i, vp, vp]),
+    "davf_head_bwd": (i, [vp, vp, vp, i, i, i, vp, vp, vp, vp]),
 }
 
 _lib = None

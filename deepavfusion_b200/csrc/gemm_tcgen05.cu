@@ -47,7 +47,7 @@ __host__ __device__ constexpr int fit_stages(int want, int epi, int ew, int bn, 
   const int avail = 232448 - 1024 - 16 - 8 * (2 * want + 5 + ew) - (int)ones_bytes(epi) - (int)staging_bytes(epi, ew);
   return avail / stage < want ? avail / stage : want;
 }
-constexpr uint32_t kOnesBytes = 2048;                  // all-ones bf16 B tile (N=16, K=16) for the row-sum MMA
+
 constexpr int kMaxGroup = 6;                          // problems per grouped launch (kernel parameter block ~2.6 KB)
 constexpr uint32_t kSpinLimit = 4000000u;   // try_wait calls before giving up (seconds): trap instead of hanging the GPU
 
@@ -382,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
     for (int w = 0; w < EW; ++w) mbar_init(aux_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (want_rowsum) {      // bf16 1.0 everywhere: layout-agnostic B operand
+  if constexpr (ones_bytes(EPI) > 0) if (want_rowsum) {      // bf16 1.0 everywhere: layout-agnostic B operand
     for (uint32_t i = threadIdx.x; i < ones_bytes(EPI) / 4; i += blockDim.x)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(ones_base + 4 * i), "r"(0x3F803F80u) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma

@@ -561,3 +561,45 @@ class PredLossFn(torch.autograd.Function):
                         st.grad(m.norm_w), st.grad(m.norm_b), dx0_out=dseq[:, nF:])
         _done(m)
         return dseq, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a11  classifier tail: tokens.mean(1) -> BatchNorm1d(affine=False) -> Linear      classifier.py:49-58
+# --------------------------------------------------------------------------------------------
+class ClassifierTailFn(torch.autograd.Function):
+    """All f32 (the reference runs this path without autocast).  ``anchor`` (the head weight) makes autograd
+    record the node when the encoder is frozen and ``x`` carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, anchor: Tensor, m: SimpleNamespace, bn_training: bool):
+        x = x.contiguous()
+        B, n, D = x.shape
+        pooled = K.meanpool_fwd(x)
+        mean = rstd = None
+        feat = pooled
+        if m.bn is not None:
+            bn = m.bn
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            feat, mean, rstd = K.batchnorm1d_fwd(pooled, bn.running_mean, bn.running_var, bn_training, momentum, bn.eps)
+            if bn_training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        y = K.head_fwd(feat, m.head_w.data, m.head_b.data)
+        ctx.m, ctx.n, ctx.bn_training = m, n, bn_training
+        ctx.save_for_backward(pooled, feat, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        m = ctx.m
+        st: ParamStore = m.store
+        pooled, feat, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        need_dx = ctx.needs_input_grad[0]
+        dfeat = K.head_bwd(dy, feat, m.head_w.data,
+                           st.grad(m.head_w) if m.head_w.requires_grad else None,
+                           st.grad(m.head_b) if m.head_b.requires_grad else None, need_dx)
+        _done(m)
+        if not need_dx:
+            return None, None, None, None
+        dpool = K.batchnorm1d_bwd(dfeat, pooled, mean, rstd, ctx.bn_training) if m.bn is not None else dfeat
+        return K.meanpool_bwd(dpool, ctx.n), None, None, None

@@ -422,6 +422,68 @@ def sumsq_f32(g: Tensor, out: Tensor) -> None:
           "davf_sumsq_f32")
 
 
+# --------------------------------------------------------------------------------------------
+# a11 classifier tail (f32)
+# --------------------------------------------------------------------------------------------
+def meanpool_fwd(x: Tensor) -> Tensor:
+    """x f32 [B, n, D] (dense rows, any batch stride) -> [B, D] mean over the tokens (classifier.py:49)."""
+    _need(x, torch.float32, "x", contiguous=False)
+    B, n, D = x.shape
+    assert x.stride(2) == 1 and x.stride(1) == D
+    out = torch.empty(B, D, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().davf_meanpool_fwd(_ptr(x), x.stride(0), B, n, D, _ptr(out), _stream()), "davf_meanpool_fwd")
+    return out
+
+
+def meanpool_bwd(dy: Tensor, n: int) -> Tensor:
+    _need(dy, torch.float32, "dy")
+    B, D = dy.shape
+    dx = torch.empty(B, n, D, dtype=torch.float32, device=dy.device)
+    check(_cabi.lib().davf_meanpool_bwd(_ptr(dy), B, n, D, _ptr(dx), _stream()), "davf_meanpool_bwd")
+    return dx
+
+
+def batchnorm1d_fwd(x: Tensor, running_mean: Tensor, running_var: Tensor, training: bool, momentum: float, eps: float):
+    """BatchNorm1d(affine=False) on [B, D]; returns (y, save_mean, save_rstd); running stats updated in place when training."""
+    _need(x, torch.float32, "x")
+    B, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(D, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(D, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().davf_batchnorm1d_fwd(_ptr(x), B, D, int(training), _ptr(_need(running_mean, torch.float32, "running_mean")),
+                                           _ptr(_need(running_var, torch.float32, "running_var")), float(momentum), float(eps),
+                                           _ptr(y), _ptr(mean), _ptr(rstd), _stream()), "davf_batchnorm1d_fwd")
+    return y, mean, rstd
+
+
+def batchnorm1d_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, training: bool) -> Tensor:
+    _need(dy, torch.float32, "dy"); _need(x, torch.float32, "x")
+    B, D = x.shape
+    dx = torch.empty_like(x)
+    check(_cabi.lib().davf_batchnorm1d_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), B, D, int(training), _ptr(dx), _stream()), "davf_batchnorm1d_bwd")
+    return dx
+
+
+def head_fwd(x: Tensor, W: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """y = x W^T + bias, f32, any number of classes."""
+    _need(x, torch.float32, "x"); _need(W, torch.float32, "W")
+    B, D = x.shape
+    Cn = W.shape[0]
+    y = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
+    check(_cabi.lib().davf_head_fwd(_ptr(x), _ptr(W), _ptr(bias), B, Cn, D, _ptr(y), _stream()), "davf_head_fwd")
+    return y
+
+
+def head_bwd(dy: Tensor, x: Tensor, W: Tensor, dW: Optional[Tensor], db: Optional[Tensor], need_dx: bool) -> Optional[Tensor]:
+    """dW += dy^T x, db += colsum dy (in place, either may be None); returns dx = dy W or None."""
+    _need(dy, torch.float32, "dy"); _need(x, torch.float32, "x"); _need(W, torch.float32, "W")
+    B, D = x.shape
+    Cn = W.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    check(_cabi.lib().davf_head_bwd(_ptr(dy), _ptr(x), _ptr(W), B, Cn, D, _ptr(dW), _ptr(db), _ptr(dx), _stream()), "davf_head_bwd")
+    return dx
+
+
 def launch_count() -> int:
     return int(_cabi.lib().davf_launch_count())
 

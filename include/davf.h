@@ -256,6 +256,22 @@ int davf_sumsq_f32(const float* g, int64_t n, float* out, davf_stream_t s);
 /* Plain f32 -> bf16 cast of a flat buffer (weight refresh after load_state_dict). */
 int davf_cast_flat_bf16(const float* src, davf_bf16* dst, int64_t n, davf_stream_t s);
 
+/* ---- a11: classifier tail (reference models/classifier.py:42-59) -------------------------------
+ * x.mean(dim=1) over the tokens, BatchNorm1d(embed_dim, affine=False, eps=1e-6) on the pooled features
+ * (classifier.py:15-18,50-54; training mode updates running_mean / running_var with `momentum`, unbiased variance,
+ * as torch does) and the three nn.Linear heads (:20-22,56-58).  All f32 (the reference runs lin-probe / fine-tune
+ * with use_amp = False).  C (classes) is arbitrary: 310, 527, ... */
+int davf_meanpool_fwd(const float* x, int64_t batch_stride, int B, int n, int D, float* out, davf_stream_t s);
+int davf_meanpool_bwd(const float* dy, int B, int n, int D, float* dx, davf_stream_t s);
+int davf_batchnorm1d_fwd(const float* x, int B, int D, int training, float* running_mean, float* running_var,
+                         float momentum, float eps, float* y, float* save_mean, float* save_rstd, davf_stream_t s);
+int davf_batchnorm1d_bwd(const float* dy, const float* x, const float* mean, const float* rstd, int B, int D, int training,
+                         float* dx, davf_stream_t s);
+/* y[b,c] = x[b,:] . W[c,:] + bias[c];  backward: dW += dy^T x, db += colsum dy (both optional), dx = dy W (optional) */
+int davf_head_fwd(const float* x, const float* W, const float* bias, int B, int C, int D, float* y, davf_stream_t s);
+int davf_head_bwd(const float* dy, const float* x, const float* W, int B, int C, int D, float* dW, float* db, float* dx,
+                  davf_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

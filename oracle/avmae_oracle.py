@@ -448,6 +448,62 @@ def loss_and_grads(sd: Dict[str, Tensor], cfg: OracleConfig, image, audio, noise
 
 
 # --------------------------------------------------------------------------------------
+# a11: AVClassifier  (classifier.py:42-59)
+# --------------------------------------------------------------------------------------
+def classifier_state(cfg: OracleConfig, num_classes: int, seed: int = 0, input_norm: bool = False) -> Dict[str, Tensor]:
+    """Encoder part of ``build_state`` (keys ``encoder.*``) plus the heads (classifier.py:20-22) and, with
+    ``input_norm``, the BatchNorm1d buffers (:15-18)."""
+    sd = {k: v for k, v in build_state(cfg, seed=seed).items() if k.startswith("encoder.")}
+    g = torch.Generator().manual_seed(seed + 101)
+    for m in ("image", "audio", "fusion"):
+        sd[f"{m}_head.weight"] = torch.randn(num_classes, cfg.dim, generator=g) * 0.05
+        sd[f"{m}_head.bias"] = torch.randn(num_classes, generator=g) * 0.05
+        if input_norm:
+            sd[f"{m}_norm.running_mean"] = torch.zeros(cfg.dim)
+            sd[f"{m}_norm.running_var"] = torch.ones(cfg.dim)
+            sd[f"{m}_norm.num_batches_tracked"] = torch.tensor(0)
+    return sd
+
+
+def classifier_forward(sd: Dict[str, Tensor], cfg: OracleConfig, image: Tensor, audio: Tensor, input_norm: bool = False,
+                       training: bool = True, freeze_encoder: bool = False, momentum: float = 0.1, eps: float = 1e-6):
+    """Returns (pred_image, pred_audio, pred_fusion) and the updated BatchNorm running statistics.  The reference
+    runs this path in fp32 (configs/linprobe.yaml:35, finetune.yaml:50)."""
+    P = _Prec(False)
+    if freeze_encoder:                                                                    # :43-45
+        with torch.no_grad():
+            xs = encoder_forward(P, sd, cfg, image, audio)
+    else:
+        xs = encoder_forward(P, sd, cfg, image, audio)                                    # :47
+    preds, stats = [], {}
+    for m, x in zip(("image", "audio", "fusion"), xs):
+        f = x.mean(dim=1)                                                                 # :49
+        if input_norm:                                                                    # :50-54, nn.BatchNorm1d(affine=False)
+            rm, rv = sd[f"{m}_norm.running_mean"], sd[f"{m}_norm.running_var"]
+            if training:
+                mu, var = f.mean(0), f.var(0, unbiased=False)
+                stats[f"{m}_norm.running_mean"] = (1 - momentum) * rm + momentum * mu.detach()
+                stats[f"{m}_norm.running_var"] = (1 - momentum) * rv + momentum * f.var(0, unbiased=True).detach()
+            else:
+                mu, var = rm, rv
+            f = (f - mu) / torch.sqrt(var + eps)
+        preds.append(F.linear(f, sd[f"{m}_head.weight"], sd[f"{m}_head.bias"]))           # :56-58
+    return tuple(preds), stats
+
+
+def classifier_loss_and_grads(sd, cfg, image, audio, target_w, input_norm=False, training=True, freeze_encoder=False):
+    """Scalar = sum_m (pred_m * target_w).sum() -- a fixed linear functional of the three predictions, so that the
+    gradient check does not depend on a loss the path does not own.  Returns (preds, stats, grads)."""
+    trainable = lambda k: (k not in FROZEN_KEYS) and ("running_" not in k) and ("num_batches" not in k) and \
+        not (freeze_encoder and k.startswith("encoder."))
+    leaves = {k: (v.detach().clone().requires_grad_(True) if (v.is_floating_point() and trainable(k)) else v) for k, v in sd.items()}
+    preds, stats = classifier_forward(leaves, cfg, image, audio, input_norm, training, freeze_encoder)
+    sum((p * target_w).sum() for p in preds).backward()
+    grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}
+    return tuple(p.detach() for p in preds), stats, grads
+
+
+# --------------------------------------------------------------------------------------
 # a9: AdamW restatement (torch.optim.AdamW single-tensor math, used by train.py:93 with betas (.9,.95))
 # --------------------------------------------------------------------------------------
 def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float, beta2: float,

@@ -179,6 +179,60 @@ def run_config(name, cfg, B, out_dir):
     return meta
 
 
+def classifier_fixture(out_dir):
+    """a11: the oracle's AVClassifier restatement against the REAL reference classifier (models/classifier.py) on a
+    small encoder (dims of tests/model_utils.tiny_cfg), lin-probe (frozen, BatchNorm) and fine-tune (trainable)."""
+    from functools import partial
+    from models.deepavfusion import DeepAVFusion   # reference
+    from models.classifier import AVClassifier     # reference
+    import models.vits as ref_vits                 # reference
+    cfg = O.OracleConfig(image_size=(64, 64), audio_size=(32, 96), dim=128, depth=2, heads=2, fusion_heads=2,
+                         dec_dim=128, dec_depth=2, dec_heads=4, fusion_attn_ratio=0.25, fusion_mlp_ratio=1.0)   # = tests/model_utils.tiny_cfg()
+
+    def ref_arch(pretrained=None, **kw):           # a small reference ViT (the reference only registers base / large / huge)
+        return ref_vits.ViT(patch_size=cfg.patch, embed_dim=cfg.dim, depth=cfg.depth, num_heads=cfg.heads, mlp_ratio=cfg.mlp_ratio,
+                            norm_layer=partial(torch.nn.LayerNorm, eps=cfg.enc_eps), **kw)
+    ref_vits.__dict__["vit_test"] = ref_arch
+    C, B = 10, 4
+    image, audio = make_inputs(cfg, B)
+    g = torch.Generator().manual_seed(5)
+    tw = torch.randn(B, C, generator=g)
+    saved = {}
+    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False)):
+        torch.manual_seed(0)
+        enc = DeepAVFusion(image_arch="vit_test", image_pretrained="", image_size=cfg.image_size,
+                           audio_arch="vit_test", audio_pretrained="", audio_size=cfg.audio_size,
+                           fusion_arch="factorized_mmi", fusion_layers=cfg.fusion_layers, num_fusion_tkns=cfg.fusion_tkns,
+                           fusion_mlp_ratio=cfg.fusion_mlp_ratio, fusion_attn_ratio=cfg.fusion_attn_ratio, fusion_num_heads=cfg.fusion_heads)
+        model = AVClassifier(enc, C, freeze_encoder=freeze, input_norm=inorm)
+        sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
+        assert set(sd) == set(model.state_dict()), set(sd) ^ set(model.state_dict())
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        preds = model(image, audio)
+        sum((p * tw).sum() for p in preds).backward()
+        ref_grads = {k: p.grad for k, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+        opreds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
+        for a, b in zip(opreds, preds):
+            assert rel(a, b.detach()) < 1e-5, (tag, rel(a, b.detach()))
+        assert set(grads) == set(ref_grads), (tag, set(grads) ^ set(ref_grads))
+        worst = max(rel(grads[k], ref_grads[k]) if ref_grads[k].norm() > 1e-7 else float((grads[k] - ref_grads[k]).abs().max()) for k in ref_grads)
+        assert worst < 2e-4, (tag, worst)
+        msd = model.state_dict()
+        for k, v in stats.items():
+            assert rel(v, msd[k]) < 1e-5, (tag, k)
+        print(f"[classifier/{tag}] oracle == reference: preds ok, {len(grads)} grads, worst rel err {worst:.2e}")
+        for n, pr in zip(("image", "audio", "fusion"), preds):
+            saved[f"{tag}_pred_{n}"] = pr.detach().numpy()
+        keys = sorted(ref_grads)
+        saved[f"{tag}_grad_norms"] = np.array([float(ref_grads[k].double().norm()) for k in keys])
+        saved[f"{tag}_grad_keys"] = np.array(keys)
+        for k, v in stats.items():
+            saved[f"{tag}_{k}"] = msd[k].numpy()
+    saved["target_w"] = tw.numpy()
+    np.savez_compressed(os.path.join(out_dir, "classifier_tiny.npz"), **saved)
+
+
 def mask_ties_fixture(out_dir):
     """Ties: the reference calls argsort without stable=True (avmae.py:128-129); on CPU its result
     is recorded here next to the stable definition the build uses."""
@@ -198,6 +252,9 @@ def mask_ties_fixture(out_dir):
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "classifier":      # only the (cheap) classifier fixture
+        classifier_fixture(out_dir)
+        return
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     m1 = run_config("vggsound_b2", O.OracleConfig(fusion_attn_ratio=0.25, fusion_mlp_ratio=1.0), 2, out_dir)
     assert m1["n_params"] == 320_563_712, m1["n_params"]             # SURVEY.md 8(c) KAT
@@ -205,6 +262,7 @@ def main():
     assert m2["n_params"] == 378_997_760, m2["n_params"]
     m3 = run_config("sparse_fusion_b1", O.OracleConfig(fusion_attn_ratio=0.25, fusion_mlp_ratio=1.0, fusion_layers="0-3-7"), 1, out_dir)
     mask_ties_fixture(out_dir)
+    classifier_fixture(out_dir)
     print("param counts:", m1["n_params"], m2["n_params"], m3["n_params"])
 
 

@@ -278,6 +278,46 @@ def sumsq_f32(g, out):
     out += (g.double() ** 2).sum().float()
 
 
+def meanpool_fwd(x):
+    return x.float().mean(dim=1)
+
+
+def meanpool_bwd(dy, n):
+    return (dy / n)[:, None, :].expand(-1, n, -1).contiguous()
+
+
+def batchnorm1d_fwd(x, running_mean, running_var, training, momentum, eps):
+    B = x.shape[0]
+    if training:
+        mean, var = x.mean(0), x.var(0, unbiased=False)
+        running_mean.mul_(1 - momentum).add_(momentum * mean)
+        running_var.mul_(1 - momentum).add_(momentum * (x.var(0, unbiased=True) if B > 1 else var))
+    else:
+        mean, var = running_mean.clone(), running_var.clone()
+    rstd = (var + eps).rsqrt()
+    return (x - mean) * rstd, mean, rstd
+
+
+def batchnorm1d_bwd(dy, x, mean, rstd, training):
+    if not training:
+        return dy * rstd
+    xh = (x - mean) * rstd
+    return rstd * (dy - dy.mean(0) - xh * (dy * xh).mean(0))
+
+
+def head_fwd(x, W, bias):
+    y = x @ W.t()
+    return y + bias if bias is not None else y
+
+
+def head_bwd(dy, x, W, dW, db, need_dx):
+    if dW is not None:
+        dW += dy.t() @ x
+    if db is not None:
+        db += dy.sum(0)
+    return dy @ W if need_dx else None
+
+
 def launch_count():
     return 0
 

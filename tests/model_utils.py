@@ -36,6 +36,13 @@ def build_model(cfg: O.OracleConfig, device="cpu"):
     return model.to(device)
 
 
+def build_classifier(cfg: O.OracleConfig, num_classes: int, freeze_encoder: bool, input_norm: bool, device="cpu"):
+    """Our drop-in AVClassifier(DeepAVFusion) for an oracle config."""
+    from deepavfusion_b200.models import AVClassifier
+    enc = build_model(cfg, "cpu").encoder
+    return AVClassifier(enc, num_classes, freeze_encoder=freeze_encoder, input_norm=input_norm).to(device)
+
+
 def make_inputs(cfg, B, seed=1):
     g = torch.Generator().manual_seed(seed)
     image = torch.randn(B, cfg.image_chans, *cfg.image_size, generator=g)

@@ -354,3 +354,30 @@ def test_adamw_and_sumsq(K):
     close(v[:frozen0], torch.cat(Vo), 1e-5, 1e-10, "adamw v")
     assert torch.equal(p[frozen0:], p_frozen) and float(m[frozen0:].abs().max()) == 0
     assert torch.equal(pb.cpu(), p.cpu().to(bf16))
+
+
+# ---------------------------------------------------------------- a11 classifier tail (f32)
+@pytest.mark.parametrize("B,n,D,C", [(32, 196, 768, 310), (5, 32, 128, 10), (256, 96, 768, 527)])
+def test_classifier_tail_kernels(K, B, n, D, C):
+    x = rnd(B, n + 3, D, seed=40)[:, 3:]                      # dense rows, batch stride != n * D
+    pooled = K.meanpool_fwd(x)
+    close(pooled, E.meanpool_fwd(x.cpu()), 1e-5, 1e-5, "meanpool")
+    dy = rnd(B, D, seed=41)
+    close(K.meanpool_bwd(dy, n), E.meanpool_bwd(dy.cpu(), n), 1e-6, 1e-7, "meanpool bwd")
+    for training in (True, False):
+        rm, rv = rnd(D, seed=42) * 0.1, rnd(D, seed=43).abs() + 0.5
+        erm, erv = rm.cpu().clone(), rv.cpu().clone()
+        y, mean, rstd = K.batchnorm1d_fwd(pooled, rm, rv, training, 0.1, 1e-6)
+        ey, emean, erstd = E.batchnorm1d_fwd(pooled.cpu(), erm, erv, training, 0.1, 1e-6)
+        close(y, ey, 1e-4, 1e-4, "bn y"); close(rm, erm, 1e-5, 1e-6, "running_mean"); close(rv, erv, 1e-4, 1e-6, "running_var")
+        close(K.batchnorm1d_bwd(dy, pooled, mean, rstd, training), E.batchnorm1d_bwd(dy.cpu(), pooled.cpu(), emean, erstd, training), 1e-3, 1e-4, "bn bwd")
+    W, b = rnd(C, D, seed=44, scale=0.05), rnd(C, seed=45)
+    out = K.head_fwd(pooled, W, b)
+    close(out, E.head_fwd(pooled.cpu(), W.cpu(), b.cpu()), 1e-4, 1e-4, "head fwd")
+    dout = rnd(B, C, seed=46)
+    dW, db = torch.ones(C, D, device="cuda"), torch.ones(C, device="cuda")
+    edW, edb = torch.ones(C, D), torch.ones(C)
+    dx = K.head_bwd(dout, pooled, W, dW, db, True)
+    edx = E.head_bwd(dout.cpu(), pooled.cpu(), W.cpu(), edW, edb, True)
+    close(dx, edx, 1e-4, 1e-4, "head dx"); close(dW, edW, 1e-4, 1e-3, "head dW"); close(db, edb, 1e-4, 1e-3, "head db")
+    assert K.head_bwd(dout, pooled, W, None, None, False) is None

@@ -45,6 +45,28 @@ def test_tiny_fwd_bwd_vs_oracle(name, kw, B):
     assert glob <= 2e-2, glob
 
 
+@pytest.mark.parametrize("tag,freeze,inorm", [("linprobe", True, True), ("finetune", False, False), ("finetune_bn", False, True)])
+def test_classifier_vs_oracle(tag, freeze, inorm):
+    """a11 / BASELINE configs 4-5 at test size: drop-in AVClassifier on cuda:0 (unmasked encoder + pool / BatchNorm /
+    heads, forward and backward, then eval mode on the running statistics) against the oracle restatement."""
+    from test_host_cpu import _classifier_case
+    _classifier_case("cuda", freeze, inorm)
+
+
+def test_classifier_golden_linprobe():
+    """Predictions of the REAL reference classifier (tests/golden/classifier_tiny.npz) from the CUDA path."""
+    z = np.load(os.path.join(GOLD, "classifier_tiny.npz"))
+    cfg = U.tiny_cfg()
+    image, audio = U.make_inputs(cfg, 4)
+    model = U.build_classifier(cfg, 10, True, True, "cuda")
+    model.load_state_dict(O.classifier_state(cfg, 10, seed=0, input_norm=True), strict=True)
+    model.train()
+    preds = model(image.cuda(), audio.cuda())
+    for n, p in zip(("image", "audio", "fusion"), preds):
+        ref = torch.from_numpy(z[f"linprobe_pred_{n}"])
+        assert float((p.detach().cpu() - ref).norm() / ref.norm()) < 2e-2
+
+
 def test_vitb_golden_fwd_bwd():
     """BASELINE config 1 (ViT-B, r=.25, mlp 1, B=2) against the fixture written from the REAL reference."""
     meta = json.load(open(os.path.join(GOLD, "vggsound_b2.json")))

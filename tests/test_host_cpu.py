@@ -50,6 +50,52 @@ def test_model_orchestration_vs_oracle(emulated, kw, B):
     assert named["encoder.image.pos_embed"].grad is None
 
 
+@pytest.mark.parametrize("tag,freeze,inorm", [("linprobe", True, True), ("finetune", False, False), ("finetune_bn", False, True)])
+def test_classifier_orchestration_vs_oracle(emulated, tag, freeze, inorm):
+    """a11 (classifier.py:42-59): drop-in AVClassifier, emulated kernels, against the oracle restatement."""
+    _classifier_case("cpu", freeze, inorm)
+
+
+def _classifier_case(device, freeze, inorm, C=10, B=4):
+    cfg = U.tiny_cfg()
+    sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
+    image, audio = U.make_inputs(cfg, B)
+    tw = torch.randn(B, C, generator=torch.Generator().manual_seed(5))
+    preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
+    model = U.build_classifier(cfg, C, freeze, inorm, device)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    assert model.train() is None                   # reference quirk: AVClassifier.train() returns None (classifier.py:61-64)
+    assert model.encoder.training == (not freeze)
+    out = model(image.to(device), audio.to(device))
+    sum((p * tw.to(device)).sum() for p in out).backward()
+    for p, r in zip(out, preds):
+        rel = float((p.detach().cpu() - r).norm() / r.norm())
+        assert rel < 2e-2, rel                      # bf16 encoder, f32 tail
+    named = dict(model.named_parameters())
+    assert {k for k, p in named.items() if p.requires_grad and p.grad is not None and p.grad.abs().sum() > 0} >= \
+        {k for k in grads if "head" in k}
+    gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
+    for k in grads:
+        if "head" in k or not freeze:
+            g, r = named[k].grad.detach().cpu(), grads[k]
+            # mathematically-zero gradients (e.g. the final LayerNorm bias in front of a BatchNorm) are round-off: absolute bound
+            assert float((g - r).norm()) < 6e-2 * float(r.norm()) + 1e-4 * gnorm, (k, float((g - r).norm()), float(r.norm()))
+    msd = model.state_dict()
+    for k, v in stats.items():
+        assert float((msd[k].cpu() - v).norm() / v.norm()) < 2e-2, k
+    if inorm:
+        assert int(msd["image_norm.num_batches_tracked"]) == 1
+    # eval mode uses the running statistics (no update)
+    model.eval()
+    with torch.no_grad():
+        e1 = model(image.to(device), audio.to(device))
+    epreds, _ = O.classifier_forward({**sd, **stats}, cfg, image, audio, input_norm=inorm, training=False)
+    for p, r in zip(e1, epreds):
+        assert float((p.cpu() - r).norm() / r.norm()) < 3e-2
+    return model
+
+
 def test_gradient_accumulation_and_zero_grad(emulated):
     cfg = U.tiny_cfg()
     model = U.build_model(cfg)

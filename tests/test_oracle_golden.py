@@ -89,3 +89,26 @@ def test_adamw_restatement_matches_torch():
         opt.step()
         O.adamw_step(mine, g, m, v, step, 1e-3, 0.9, 0.95, 1e-8, 0.05)
     assert (mine - ref.detach()).abs().max().item() < 1e-6
+
+
+def test_classifier_oracle_matches_reference_fixture():
+    """a11: oracle AVClassifier restatement vs outputs of the real reference classifier (tests/golden/classifier_tiny.npz,
+    written by oracle/make_golden.py): predictions, gradient norms and BatchNorm running statistics."""
+    import model_utils as U
+    z = np.load(os.path.join(GOLD, "classifier_tiny.npz"))
+    cfg = U.tiny_cfg()
+    C, B = 10, 4
+    image, audio = U.make_inputs(cfg, B)
+    tw = torch.from_numpy(z["target_w"])
+    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False)):
+        sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
+        preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
+        for n, p in zip(("image", "audio", "fusion"), preds):
+            ref = torch.from_numpy(z[f"{tag}_pred_{n}"])
+            assert float((p - ref).norm() / ref.norm()) < 1e-5
+        keys = [str(k) for k in z[f"{tag}_grad_keys"]]
+        assert sorted(grads) == keys
+        mine = np.array([float(grads[k].double().norm()) for k in keys])
+        np.testing.assert_allclose(mine, z[f"{tag}_grad_norms"], rtol=1e-4, atol=1e-7)
+        for k, v in stats.items():
+            np.testing.assert_allclose(v.numpy(), z[f"{tag}_{k}"], rtol=1e-5, atol=1e-7)

@@ -17,7 +17,7 @@ cases = {
 which = [a for a in sys.argv[1:] if a in cases] or ([] if 'timeline' in sys.argv else list(cases))
 for name in which:
     f = cases[name]
-    for _ in range(3):
+    for _ in range(int(os.environ.get("PROBE_REPS", "3"))):
         f()
     torch.cuda.synchronize()
     print("ran", name)
