@@ -98,7 +98,10 @@ class DeepAVFusion(nn.Module):
             return None
         st = self.__dict__.get("_davf_streams")
         if st is None or st[0].device != device:
-            st = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            # The fusion block is the longest dependent chain of a layer (many small kernels): its stream gets the
+            # higher priority, so its CTAs are dispatched first whenever a persistent GEMM of another branch retires.
+            prio = int(os.environ.get("DAVF_FUSION_PRIORITY", "-1"))
+            st = (torch.cuda.Stream(device), torch.cuda.Stream(device, priority=prio))
             self.__dict__["_davf_streams"] = st
         store = self.__dict__.get("_davf_store")
         if store is not None:

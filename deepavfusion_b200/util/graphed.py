@@ -60,9 +60,9 @@ class GraphedTrainStep:
             if not capturing:
                 self._reduce_and_step(sync_hp)
             return li.detach(), la.detach(), tr.optimizer.grad_norm()
-        tr.backward(li + la)
-        tr.optimizer.step(zero_grad=True, sync_hp=sync_hp)
-        tr.accums = 0
+        n0 = int(tr.n_steps)
+        tr._step(li + la, sync_hp=sync_hp)               # backward (+ bucket all-reduce) with the optimizer applied bucket by bucket
+        tr.n_steps.fill_(n0)                              # __call__ counts the steps
         return li.detach(), la.detach(), tr.optimizer.grad_norm()
 
     def _reduce_and_step(self, sync_hp: bool = True):

@@ -11,6 +11,7 @@ weight refresh are ONE fused kernel.  The two per-step host syncs of the referen
 from __future__ import annotations
 
 import contextlib
+import os
 import math
 
 import torch
@@ -44,7 +45,10 @@ class Trainer:
         self.scaler = None
         self.accum_iter = accum_iter
         self.accums = 0
-        self.sync = dist_utils.GradSync(self.store, bucket_mb=bucket_mb) if self.distributed else None
+        # bucket scheduler: gradient all-reduce (N > 1) and / or the optimizer step overlapped with backward
+        overlap_opt = isinstance(self.optimizer, FusedAdamW) and self.store.flat_g.is_cuda and os.environ.get("DAVF_OVERLAP_ADAMW", "1") != "0"
+        self.sync = dist_utils.GradSync(self.store, bucket_mb=bucket_mb, optimizer=self.optimizer if overlap_opt else None) \
+            if (self.distributed or overlap_opt) else None
         if self.distributed:
             self.broadcast_parameters()
         world = dist_utils.get_world_size() if self.distributed else 1
@@ -73,10 +77,13 @@ class Trainer:
     def get_scale(self):
         return 1.0
 
-    def backward(self, loss, create_graph=False):
+    def backward(self, loss, create_graph=False, _fuse_optimizer=False, _sync_hp=True):
         assert not create_graph
         if self.sync is not None:
             self.sync.enabled = self.accums == self.accum_iter - 1       # all-reduce on the last micro-step only
+            if _fuse_optimizer and self.sync.enabled and self.sync.optimizer is not None:
+                self.optimizer.begin_step(sync_hp=_sync_hp)              # the step is applied bucket by bucket during backward
+                self.sync.fuse_optimizer = True
         loss.backward()
         self.store.join_side_streams(torch.cuda.current_stream() if self.store.flat_g.is_cuda else None)
         if self.sync is not None:
@@ -86,10 +93,15 @@ class Trainer:
     def step(self, loss, create_graph=False, clip_grad=None, skip_grad=None):
         if clip_grad is not None or skip_grad is not None:
             raise NotImplementedError("clip_grad / skip_grad are unset in every pre-training config (deepavfusion.yaml:60)")
-        self.backward(loss, create_graph=create_graph)
+        return self._step(loss)
+
+    def _step(self, loss, sync_hp=True):
+        fused = self.sync is not None and self.sync.optimizer is not None
+        self.backward(loss, _fuse_optimizer=fused, _sync_hp=sync_hp)
         norm = None
         if self.accums == self.accum_iter:
-            self.optimizer.step(zero_grad=True)        # /accum/world, grad-norm^2, AdamW, bf16 refresh, zero_grad
+            if not fused:
+                self.optimizer.step(zero_grad=True, sync_hp=sync_hp)   # /accum/world, grad-norm^2, AdamW, bf16 refresh, zero_grad
             norm = self.optimizer.grad_norm()
             self.accums = 0
             self.n_steps += 1

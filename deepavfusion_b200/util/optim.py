@@ -51,6 +51,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._beta_mul = torch.tensor([b1, b2, 1.0, 1.0], dtype=torch.float32, device=dev)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.n_steps = 0
+        self._open = False
 
     # -- hyper-parameter upload (only when the schedule changed something) -----------------------
     def _sync_hp(self):
@@ -67,19 +68,40 @@ class FusedAdamW(torch.optim.Optimizer):
         self.scal[2] = scale
 
     @torch.no_grad()
-    def step(self, closure=None, zero_grad: bool = True, sync_hp: bool = True):
-        """One fused launch: p, m, v update (+bf16 shadow, +grad-norm^2, +zero_grad)."""
-        assert closure is None
+    def begin_step(self, sync_hp: bool = True):
+        """Opens an optimizer step that is applied bucket by bucket while backward still runs (``step_range``,
+        driven by ``GradSync``): advances beta^t and clears the grad-norm accumulator once."""
         if sync_hp:
             self._sync_hp()
         self.scal.mul_(self._beta_mul)                      # beta^t on the device
         self.grad_sumsq.zero_()
+        self._open = True
+
+    @torch.no_grad()
+    def step_range(self, lo: int, hi: int, zero_grad: bool = True):
+        """The fused update on elements [lo, hi) of the flat buffers (a gradient bucket whose values are final)."""
+        assert self._open and lo % ALIGN == 0 and hi % ALIGN == 0
         b1, b2 = self.param_groups[0]["betas"]
         st = self.store
-        K.adamw_step(st.flat_p, st.flat_g, self.flat_m, self.flat_v, st.flat_lp, self.chunk_group, self.hp, self.scal,
+        K.adamw_step(st.flat_p[lo:hi], st.flat_g[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi], st.flat_lp[lo:hi],
+                     self.chunk_group[lo // ALIGN:hi // ALIGN], self.hp, self.scal,
                      float(b1), float(b2), float(self.param_groups[0]["eps"]), zero_grad, self.grad_sumsq)
-        st.mark_lowp_fresh()
+
+    @torch.no_grad()
+    def end_step(self):
+        """Closes a bucketed step (every range has been launched)."""
+        assert self._open
+        self._open = False
+        self.store.mark_lowp_fresh()
         self.n_steps += 1
+
+    @torch.no_grad()
+    def step(self, closure=None, zero_grad: bool = True, sync_hp: bool = True):
+        """One fused launch: p, m, v update (+bf16 shadow, +grad-norm^2, +zero_grad)."""
+        assert closure is None and not self._open
+        self.begin_step(sync_hp)
+        self.step_range(0, self.store.numel, zero_grad)
+        self.end_step()
         return None
 
     def grad_norm(self) -> torch.Tensor:

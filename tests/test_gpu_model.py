@@ -150,3 +150,33 @@ def test_multistream_backward_matches_single_stream(monkeypatch):
         assert bool(torch.isfinite(g).all()), f"non-finite gradient in multi-stream iteration {it}"
         rel = ((g - ref).norm() / ref.norm()).item()
         assert rel < 1e-3, (it, rel)
+
+
+def test_overlapped_optimizer_matches_plain_step(monkeypatch):
+    """Trainer.step applies the fused AdamW bucket by bucket under backward (GradSync.fuse_optimizer); the parameters,
+    optimizer state and grad norm after two steps equal those of backward-then-one-AdamW-launch (DAVF_OVERLAP_ADAMW=0)."""
+    from deepavfusion_b200.util.misc import Trainer
+    cfg = U.tiny_cfg()
+    sd = O.build_state(cfg, seed=0)
+    image, audio = U.make_inputs(cfg, 3)
+    ni, na = U.make_noise(cfg, 3)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DAVF_OVERLAP_ADAMW", mode)
+        model = U.build_model(cfg, "cuda")
+        model.load_state_dict(sd, strict=True)
+        tr = Trainer(model, optimizer=torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05), bucket_mb=0.25)
+        assert (tr.sync is not None and tr.sync.optimizer is not None and len(tr.sync.buckets) > 3) == (mode == "1")
+        for _ in range(2):
+            with U.inject_rand([ni, na]):
+                li, la, _, _ = model(image.cuda(), audio.cuda())
+            norm, _ = tr.step(li + la)
+        torch.cuda.synchronize()
+        assert float(tr.store.flat_g.abs().max()) == 0.0          # zero_grad is part of the fused step
+        res[mode] = (tr.store.flat_p.clone(), tr.optimizer.flat_m.clone(), tr.optimizer.flat_v.clone(), float(norm), tr.optimizer.n_steps)
+    p1, m1, v1, n1, s1 = res["1"]
+    p0, m0, v0, n0, s0 = res["0"]
+    assert s1 == s0 == 2 and abs(n1 - n0) <= 1e-3 * n0
+    p_init = torch.cat([sd[k].flatten() for k in sd]).norm()
+    assert float((p1 - p0).norm()) <= 1e-5 * float(p0.norm())
+    assert float((m1 - m0).norm()) <= 1e-3 * float(m0.norm()) and float((v1 - v0).norm()) <= 1e-3 * float(v0.norm())
