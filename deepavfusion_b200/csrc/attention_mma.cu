@@ -10,6 +10,7 @@
 //
 // Strided q / k / v / o addressing (element strides per batch and per row, heads packed along the
 // row) reads packed qkv buffers and live-query sub-ranges in place and writes packed dqkv buffers.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace davf {
@@ -407,6 +408,12 @@ template <int DQK, int DV>
 static int launch_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
   if (a.Nq <= 16) return launch_fwd_nw<DQK, DV, 1>(a, st);      // fusion-token attentions: 8 / 16 queries
   if (a.Nq <= 32) return launch_fwd_nw<DQK, DV, 2>(a, st);
+  // long sequences (decoders: 228 / 128 queries): more query rows per CTA, so the head's K / V tile is staged
+  // into shared memory by fewer CTAs (DAVF_ATTN_FWD_NW = 4 / 8 / 16 overrides, for experiments)
+  static const int force = [] { const char* e = getenv("DAVF_ATTN_FWD_NW"); return e ? atoi(e) : 0; }();
+  const int nw = force ? force : (a.Nq > 64 ? 8 : 4);        // measured: decoder image 104 -> 64 us, decoder audio 30.5 -> 25.1 us
+  if (nw == 16) return launch_fwd_nw<DQK, DV, 16>(a, st);
+  if (nw == 8) return launch_fwd_nw<DQK, DV, 8>(a, st);
   return launch_fwd_nw<DQK, DV, 4>(a, st);
 }
 
