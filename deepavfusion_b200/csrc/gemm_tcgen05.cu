@@ -265,10 +265,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+// Work decomposition.  Classic: every (m, n) tile is cut into `splits` equal K ranges.  Stream-K (sk_units > 0, wgrad
+// only: partial products are f32-ADDED to the output, so any partition of the K loop is valid): the linearised
+// (tile, k-block) space is cut into sk_units equal ranges of sk_len k-blocks, one per CTA (pair); a range touches at
+// most two tiles (sk_len <= kb_total), which appear as "tile" t = unit and t = unit + sk_units (possibly empty:
+// kb1 <= kb0).  Every CTA pair then runs the same number of k-blocks, whatever the tile count.
 struct TileSched {
   int m_tiles, n_tiles, splits, kb_total, kb_per_split;
-  __device__ __forceinline__ int num_tiles() const { return m_tiles * n_tiles * splits; }
+  int sk_units, sk_len;
+  __host__ __device__ __forceinline__ int num_tiles() const { return sk_units > 0 ? 2 * sk_units : m_tiles * n_tiles * splits; }
   __device__ __forceinline__ void decode(int t, int& m_blk, int& n_blk, int& sp, int& kb0, int& kb1) const {
+    if (sk_units > 0) {
+      const int unit = t % sk_units, second = t / sk_units;
+      const int total = m_tiles * n_tiles * kb_total;
+      const int lo = unit * sk_len, hi = min(total, lo + sk_len);
+      int mn = lo / kb_total;
+      const int bnd = (mn + 1) * kb_total;
+      int a = lo, b = min(hi, bnd);
+      if (second) { a = bnd; b = hi; ++mn; }
+      kb0 = a - mn * kb_total;
+      kb1 = b - mn * kb_total;           // <= kb0 when the range does not reach a second tile
+      m_blk = mn % m_tiles;
+      n_blk = mn / m_tiles;
+      sp = kb0 == 0 ? 0 : 1;
+      return;
+    }
     sp = t % splits;
     const int mn = t / splits;
     m_blk = mn % m_tiles;
@@ -421,6 +442,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
         int p, tl, m_blk, n_blk, sp, kb0, kb1;
         locate(t, p, tl);
         gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+        if (kb1 <= kb0) continue;                   // empty stream-K segment
         const CUtensorMap* tmap_a = &gp.ta[p];
         const CUtensorMap* tmap_b = &gp.tb[p];
         const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM;      // this CTA's rows of A
@@ -460,12 +482,14 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int p, tl, m_blk, n_blk, sp, kb0, kb1;
         locate(t, p, tl);
         gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+        if (kb1 <= kb0) continue;                   // empty stream-K segment (no accumulator stage is consumed)
         const int acc = local % NACC;
         const uint32_t acc_phase = (local / NACC) & 1u;
+        ++local;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -528,11 +552,13 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
     const uint32_t my_row = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
     uint32_t aux_phase = 0;
     int local = 0, grp_count = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int m_blk, n_blk, sp, kb0, kb1;
       gp.ts[0].decode(t, m_blk, n_blk, sp, kb0, kb1);
+      if (kb1 <= kb0) continue;
       const int acc = local % NACC;
       const uint32_t acc_phase = (local / NACC) & 1u;
+      ++local;
       const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's boxes
       const int n_base = n_blk * BN + half * SLICE;
       const bool live = m0 < (int)ep.M;                // a box entirely below the matrix is neither loaded nor stored
@@ -643,14 +669,16 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
     using F = EpiSel<EPI>;
     struct Pre { float4 bias; float4 res[4]; uint2 aux[4]; };
     int local = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++local) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int p, tl, m_blk, n_blk, sp, kb0, kb1;
       locate(t, p, tl);
       gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+      if (kb1 <= kb0) continue;
       const EpiParams& ep = gp.ep[p];
       const bool has_bias = F::bias(ep), has_res = F::res(ep), has_auxin = F::dgelu(ep);
       const int acc = local % NACC;
       const uint32_t acc_phase = (local / NACC) & 1u;
+      ++local;
       const int64_t m_base = (int64_t)m_blk * (BM * CG) + cta_rank * BM + quad * 32;
       // per-tile row bookkeeping for the 4 rows this lane touches in the coalesced phase
       int64_t out_off[4], res_off[4], aux_off[4];
@@ -856,7 +884,8 @@ static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
     attr_set = true;
   }
   const int tiles = gp.tile_end[NG - 1];
-  const int clusters = tiles < kNumSMs / CG ? tiles : kNumSMs / CG;
+  int clusters = tiles < kNumSMs / CG ? tiles : kNumSMs / CG;
+  if (NG == 1 && gp.ts[0].sk_units > 0) clusters = gp.ts[0].sk_units;      // stream-K: unit u and its second segment belong to cluster u
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(kNumThreads);
@@ -902,7 +931,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSc
     }
     if (rc) return rc;
   }
-  gp.tile_end[0] = ts.m_tiles * ts.n_tiles * ts.splits;
+  gp.tile_end[0] = ts.num_tiles();
   return launch_group<BN, STAGES_, AK, BKM, EPI, CG, 1>(gp, st);
 }
 
@@ -983,18 +1012,55 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
     const int per = (kb_total + splits - 1) / splits;
     return std::make_pair((kb_total + per - 1) / per, per);      // no empty split
   };
+  // Stream-K for accumulating (wgrad) launches whose tiles do not fill the machine: equal K-block ranges per CTA (pair)
+  // instead of whole splits (DAVF_STREAMK=0 turns it off).  Needs a range no longer than one tile's K loop.
+  static const int streamk_on = [] { const char* e = getenv("DAVF_STREAMK"); return e ? atoi(e) : 1; }();
+  auto make_sched = [&](int64_t m_t, int64_t n_t, int units) {
+    const auto sp = pick_splits(m_t * n_t, units);
+    TileSched ts{(int)m_t, (int)n_t, sp.first, kb_total, sp.second, 0, 0};
+    const int64_t mn = m_t * n_t, total = mn * kb_total;
+    if (streamk_on && a.accumulate && a.split_k <= 0 && mn < units && total >= (int64_t)units * 4) {
+      int len = (int)((total + units - 1) / units);
+      if (len < 4) len = 4;
+      // cost in k-block units: a CTA (pair) runs its K range plus up to two f32 reduce epilogues against
+      // rounds x (split length + one epilogue) of the classic decomposition.  Measured on B200 (gemm_shapes_bench with
+      // DAVF_STREAMK=2): the reduce epilogue of a 256 x 256 tile costs about as much as 12 k-blocks, so for this model's
+      // wgrad shapes the balanced ranges rarely pay for the second epilogue.
+      constexpr int kEpi = 12;
+      const int64_t rounds = (mn * sp.first + units - 1) / units;
+      if (len <= kb_total && (streamk_on == 2 || len + 2 * kEpi < rounds * (sp.second + kEpi))) {     // DAVF_STREAMK=2: whenever legal (tests)
+        ts.sk_len = len;
+        ts.sk_units = (int)((total + len - 1) / len);
+      }
+    }
+    return ts;
+  };
   CUtensorMap ta, tb;
   int rc;
   // ---- CTA-pair path: 256 x 256 tiles, tcgen05.mma.cta_group::2 -----------------------------------
   static const int class_mask = [] { const char* e = getenv("DAVF_2CTA_CLASSES"); return e ? atoi(e) : 7; }();   // debug: 1 fwd, 2 dgrad, 4 wgrad
   const int cls = (a.a_kmajor && a.b_kmajor) ? 1 : (a.a_kmajor ? 2 : 4);
+  // wgrad + bias-gradient row sums: a 256-wide tile leaves no TMEM for a second accumulator stage next to the 16 row-sum
+  // columns (2 x 256 + 16 > 512), so its epilogue is not overlapped; 256 x 128 pair tiles are double-buffered
+  // (DAVF_WGRAD_ROWSUM_BN = 128 | 256, measured in tools/gemm_shapes_bench.py)
+  static const int rowsum_bn = [] { const char* e = getenv("DAVF_WGRAD_ROWSUM_BN"); return e ? atoi(e) : 256; }();
+  if (g_allow_2cta.load() && (class_mask & cls) && cls == 4 && rowsum_bn == 128 && a.rowsum_out && has_static_epi(a) && a.M >= 256 && a.N >= 128) {
+    const int64_t m2 = (a.M + 2 * BM - 1) / (2 * BM), n2 = (a.N + 127) / 128;
+    const TileSched ts = make_sched(m2, n2, kNumSMs / 2);
+    if (ts.sk_units > 0 || m2 * n2 * ts.splits >= 36) {
+      rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
+      if (rc) return rc;
+      rc = get_tensor_map(a.b, a.N, a.K, a.ldb, BK, &tb);
+      if (rc) return rc;
+      return launch_cfg<128, 6, false, false, EPI_RED | EPI_ROWSUM, 2>(ta, tb, ts, make_epi(a), st);
+    }
+  }
   if (g_allow_2cta.load() && (class_mask & cls) && has_static_epi(a) && a.M >= 256 && a.N >= 256) {
     const int64_t m2 = (a.M + 2 * BM - 1) / (2 * BM), n2 = (a.N + 255) / 256;
-    const auto sp = pick_splits(m2 * n2, kNumSMs / 2);
+    const TileSched ts = make_sched(m2, n2, kNumSMs / 2);
     // worth it when the pair tiles fill at least ~half of the 74 SM pairs; otherwise 128-wide 1-CTA tiles
     // give more parallelism
-    if (m2 * n2 * sp.first >= 36) {
-      TileSched ts{(int)m2, (int)n2, sp.first, kb_total, sp.second};
+    if (ts.sk_units >= 36 || m2 * n2 * ts.splits >= 36) {
       if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
       else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
       if (rc) return rc;
@@ -1011,8 +1077,7 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   int bn = 128;
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs && !a.rowsum_out) bn = 256;   // row-sum columns need BN = 128
   const int64_t n_tiles = (a.N + bn - 1) / bn;
-  const auto sp = pick_splits(m_tiles * n_tiles, kNumSMs);
-  TileSched ts{(int)m_tiles, (int)n_tiles, sp.first, kb_total, sp.second};
+  const TileSched ts = make_sched(m_tiles, n_tiles, kNumSMs);
   if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
   else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
   if (rc) return rc;
@@ -1049,7 +1114,7 @@ int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) 
     if (splits < 1) splits = 1;
     const int per = (kb_total + splits - 1) / splits;
     splits = (kb_total + per - 1) / per;
-    gp.ts[p] = TileSched{m_tiles, n_tiles, splits, kb_total, per};
+    gp.ts[p] = TileSched{m_tiles, n_tiles, splits, kb_total, per, 0, 0};
     if (g.a_kmajor) rc = get_tensor_map(g.a, g.K, g.M, g.lda, BM, &gp.ta[p]);
     else rc = get_tensor_map(g.a, g.M, g.K, g.lda, BK, &gp.ta[p]);
     if (rc) return rc;

@@ -241,12 +241,14 @@ sys.exit(1 if fails else 0)
 """
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
-def test_gemm_all_modes(impl):
+@pytest.mark.parametrize("impl,streamk", [(1, "1"), (0, "1"), (0, "2")], ids=["simt", "tcgen05", "tcgen05-streamk"])
+def test_gemm_all_modes(impl, streamk):
     """Runs in a subprocess: a wrong tensor-core descriptor traps (bounded mbarrier spin) and poisons
-    the CUDA context; the rest of the suite must survive that."""
+    the CUDA context; the rest of the suite must survive that.  ``streamk`` = "2" forces the stream-K work
+    decomposition of the accumulating (wgrad) launches wherever it is legal."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", GEMM_SCRIPT.format(root=root), str(impl)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", GEMM_SCRIPT.format(root=root), str(impl)], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "DAVF_STREAMK": streamk})
     print(r.stdout[-6000:]); print(r.stderr[-3000:])
     assert r.returncode == 0, "GEMM mismatches:\n" + "\n".join(l for l in r.stdout.splitlines() if l.startswith("FAIL")) + r.stderr[-1500:]
 
