@@ -117,9 +117,13 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    def mark(self):
+        """Rows sampled before this call (sampler start-up, warm-up steps) are not part of the timed region."""
+        self.start = len(self.rows)
+
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in self.rows[getattr(self, "start", 0):]:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -300,9 +304,11 @@ def run_ours(args):
 
     def dev_step():
         last["out"] = step(d_image, d_audio)
-    for _ in range(max(3, args.warmup)):
-        dev_step()
-    with ClockSampler(local) as cs:
+    with ClockSampler(local) as cs:                 # nvidia-smi needs ~0.3 s to start: launched before the warm-up steps,
+        for _ in range(max(3, args.warmup)):        # only rows sampled during the timed region are summarised
+            dev_step()
+        torch.cuda.synchronize()
+        cs.mark()
         ms = timed(dev_step, args.steps)
     clocks = cs.summary()
     li, la, norm = last["out"]
@@ -370,7 +376,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
