@@ -86,6 +86,7 @@ SIGNATURES = {
     "davf_set_gemm_impl": (i, [i]),
     "davf_get_gemm_impl": (i, []),
     "davf_set_gemm_2cta": (i, [i]),
+    "davf_set_gemm_sms": (i, [i]),
     "davf_set_attn_impl": (i, [i]),
     "davf_launch_count": (i64, []),
     "davf_mask_rank": (i, [vp, i, i, i, vp, vp, vp, vp]),

@@ -13,7 +13,8 @@ extern "C" int davf_set_gemm_impl(int impl) {
   return DAVF_OK;
 }
 extern "C" int davf_get_gemm_impl(void) { return g_gemm_impl.load(); }
-namespace davf { int gemm_set_2cta(int on); }
+namespace davf { int gemm_set_2cta(int on); int gemm_set_sms(int n); }
+extern "C" int davf_set_gemm_sms(int n) { return davf::gemm_set_sms(n); }
 extern "C" int davf_set_gemm_2cta(int on) { return davf::gemm_set_2cta(on); }
 
 static int validate_gemm(const davf_gemm_args* a) {

@@ -869,6 +869,11 @@ static int get_tensor_map(const void* ptr, int64_t inner, int64_t outer, int64_t
   return DAVF_OK;
 }
 
+// SMs the persistent GEMM grids are sized for.  Data-parallel runs leave a few SMs to the NCCL kernels that run under
+// backward: a 148-CTA persistent launch that finds some SMs taken runs its last CTAs as a second wave (davf_set_gemm_sms).
+static std::atomic<int> g_gemm_sms{[] { const char* e = getenv("DAVF_GEMM_SMS"); const int n = e ? atoi(e) : kNumSMs; return n < 2 ? 2 : (n > kNumSMs ? kNumSMs : (n & ~1)); }()};
+static inline int num_sms() { return g_gemm_sms.load(); }
+
 template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG, int NG, int EW>
 static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
   // 16 epilogue warps trade one pipeline stage for their staging (staged epilogues only)
@@ -884,7 +889,7 @@ static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
     attr_set = true;
   }
   const int tiles = gp.tile_end[NG - 1];
-  int clusters = tiles < kNumSMs / CG ? tiles : kNumSMs / CG;
+  int clusters = tiles < num_sms() / CG ? tiles : num_sms() / CG;
   if (NG == 1 && gp.ts[0].sk_units > 0) clusters = gp.ts[0].sk_units;      // stream-K: unit u and its second segment belong to cluster u
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
@@ -1046,7 +1051,7 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   static const int rowsum_bn = [] { const char* e = getenv("DAVF_WGRAD_ROWSUM_BN"); return e ? atoi(e) : 256; }();
   if (g_allow_2cta.load() && (class_mask & cls) && cls == 4 && rowsum_bn == 128 && a.rowsum_out && has_static_epi(a) && a.M >= 256 && a.N >= 128) {
     const int64_t m2 = (a.M + 2 * BM - 1) / (2 * BM), n2 = (a.N + 127) / 128;
-    const TileSched ts = make_sched(m2, n2, kNumSMs / 2);
+    const TileSched ts = make_sched(m2, n2, num_sms() / 2);
     if (ts.sk_units > 0 || m2 * n2 * ts.splits >= 36) {
       rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
       if (rc) return rc;
@@ -1057,7 +1062,7 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   }
   if (g_allow_2cta.load() && (class_mask & cls) && has_static_epi(a) && a.M >= 256 && a.N >= 256) {
     const int64_t m2 = (a.M + 2 * BM - 1) / (2 * BM), n2 = (a.N + 255) / 256;
-    const TileSched ts = make_sched(m2, n2, kNumSMs / 2);
+    const TileSched ts = make_sched(m2, n2, num_sms() / 2);
     // worth it when the pair tiles fill at least ~half of the 74 SM pairs; otherwise 128-wide 1-CTA tiles
     // give more parallelism
     if (ts.sk_units >= 36 || m2 * n2 * ts.splits >= 36) {
@@ -1075,9 +1080,9 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
   // the problem still yields at least ~one full wave of CTAs, otherwise 128 for parallelism.
   const int64_t m_tiles = (a.M + BM - 1) / BM;
   int bn = 128;
-  if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= kNumSMs && !a.rowsum_out) bn = 256;   // row-sum columns need BN = 128
+  if (a.N % 256 == 0 && m_tiles * (a.N / 256) >= num_sms() && !a.rowsum_out) bn = 256;   // row-sum columns need BN = 128
   const int64_t n_tiles = (a.N + bn - 1) / bn;
-  const TileSched ts = make_sched(m_tiles, n_tiles, kNumSMs);
+  const TileSched ts = make_sched(m_tiles, n_tiles, num_sms());
   if (a.a_kmajor) rc = get_tensor_map(a.a, a.K, a.M, a.lda, BM, &ta);
   else rc = get_tensor_map(a.a, a.M, a.K, a.lda, BK, &ta);
   if (rc) return rc;
@@ -1106,8 +1111,8 @@ int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) 
     const int kb_total = (int)((g.K + BK - 1) / BK);
     const int m_tiles = (int)((g.M + BM - 1) / BM), n_tiles = (int)((g.N + 127) / 128);
     int splits = g.split_k > 0 ? g.split_k : 1;
-    if (g.split_k <= 0 && g.accumulate && mn_total < kNumSMs) {
-      splits = (int)(kNumSMs / mn_total);
+    if (g.split_k <= 0 && g.accumulate && mn_total < num_sms()) {
+      splits = (int)(num_sms() / mn_total);
       if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
     }
     if (splits > kb_total) splits = kb_total;
@@ -1133,6 +1138,7 @@ int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) 
   return launch_group<128, 6, false, true, -1, 1, kMaxGroup>(gp, st);
 }
 
+int gemm_set_sms(int n) { g_gemm_sms.store(n < 2 ? 2 : (n > kNumSMs ? kNumSMs : (n & ~1))); return g_gemm_sms.load(); }
 int gemm_set_2cta(int on) { g_allow_2cta.store(on ? 1 : 0); return 0; }
 
 }  // namespace davf

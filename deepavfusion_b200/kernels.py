@@ -484,6 +484,11 @@ def head_bwd(dy: Tensor, x: Tensor, W: Tensor, dW: Optional[Tensor], db: Optiona
     return dx
 
 
+def set_gemm_sms(n: int) -> int:
+    """SMs the persistent GEMM grids use (see davf_set_gemm_sms); returns the value in effect."""
+    return int(_cabi.lib().davf_set_gemm_sms(int(n)))
+
+
 def launch_count() -> int:
     return int(_cabi.lib().davf_launch_count())
 

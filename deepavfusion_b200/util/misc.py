@@ -51,6 +51,9 @@ class Trainer:
             if (self.distributed or overlap_opt) else None
         if self.distributed:
             self.broadcast_parameters()
+            if self.store.flat_g.is_cuda:       # leave SMs to the NCCL kernels that run under backward (see davf_set_gemm_sms)
+                from .. import kernels as K
+                K.set_gemm_sms(148 - int(os.environ.get("DAVF_COMM_SMS", "32")))
         world = dist_utils.get_world_size() if self.distributed else 1
         if self.optimizer is not None:
             self.optimizer.set_grad_scale(1.0 / (self.accum_iter * world))

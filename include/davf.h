@@ -158,6 +158,10 @@ typedef struct {
   float* rowsum_out;
   int64_t* debug_clocks;   /* optional: 8 x i64 SM-clock timeline of CTA 0 (profiling aid), else NULL */
 } davf_gemm_args;
+/* Number of SMs the persistent GEMM grids are sized for (default: all 148; even, >= 2; returns the value in effect).
+ * Data-parallel training sets 148 - k so that the NCCL all-reduce kernels overlapped with backward (util/misc.py:32-34
+ * in the reference: DDP's bucketed reducer) do not push the last CTAs of a full-machine launch into a second wave. */
+int davf_set_gemm_sms(int n);
 int davf_gemm(const davf_gemm_args* a, davf_stream_t s);
 
 /* Grouped launch: `count` (1..DAVF_GEMM_MAX_GROUP) INDEPENDENT problems of one operand-layout class (same a_kmajor /

@@ -334,6 +334,10 @@ def set_gemm_2cta(on):
     pass
 
 
+def set_gemm_sms(n):
+    return n
+
+
 def install(monkeypatch=None):
     """Replace every kernel wrapper in deepavfusion_b200.kernels by its emulation."""
     import deepavfusion_b200.kernels as K
