@@ -90,12 +90,41 @@ def run_reference(args):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons of one GPU sampled every 50 ms during the timed region: NVML in a thread
+    (nvidia-ml-py), falling back to an `nvidia-smi -lms 100` subprocess."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.stop = [], None, gpu_index, False
+
+    def _nvml_loop(self):
+        import pynvml as N
+        h = N.nvmlDeviceGetHandleByIndex(self.idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self.stop:
+            try:
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), "0"] +
+                                 ["Active" if (r & b) else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def __enter__(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                self.idx = int(vis.split(",")[self.idx])
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -110,6 +139,7 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
