@@ -306,7 +306,7 @@ struct TileSched {
 template <int NG>
 struct GemmGroup {
   CUtensorMap ta[NG], tb[NG];
-  CUtensorMap tc, taux;              // direct (TMA) epilogue only: out / aux_out-or-aux_in as [M][N] bf16, box {64, 32}
+  CUtensorMap tc[NG], taux[NG];      // TMA epilogue: out / (aux_out | aux_in | res) as [M][N] tensors, box = 32 rows x 128 bytes
   EpiParams ep[NG];
   TileSched ts[NG];
   int tile_end[NG];
@@ -340,7 +340,7 @@ struct EpiSel {
 template <int BN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int EPI, int CG, int EW, int NG>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
-  static_assert(NG == 1 || (EPI < 0 && CG == 1), "grouped launches use the run-time-flag 1-CTA kernel");
+  static_assert(NG == 1 || EPI < 0 || (EPI & (EPI_GELU | EPI_DGELU | EPI_AUX | EPI_RES)) == 0, "grouped compile-time epilogues: bias / bf16 / f32 reduce only");
   // tile t of the launch -> problem p, tile tl of that problem
   auto locate = [&](int t, int& p, int& tl) {
     p = 0; tl = t;
@@ -547,29 +547,32 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
     static_assert(SLICE % GW == 0, "TMA epilogue works on whole boxes");
     constexpr bool kLoad = kMul || kRes;                // box1 receives a TMA load
     constexpr bool kPingPong = !kAux && !kLoad;         // both boxes serve the single output stream alternately
-    const EpiParams& ep = gp.ep[0];
     const uint32_t box0 = stage_base + (uint32_t)ew * 2u * kTmaBox, box1 = box0 + kTmaBox;
     const uint32_t my_row = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
     uint32_t aux_phase = 0;
     int local = 0, grp_count = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      int m_blk, n_blk, sp, kb0, kb1;
-      gp.ts[0].decode(t, m_blk, n_blk, sp, kb0, kb1);
+      int p, tl, m_blk, n_blk, sp, kb0, kb1;
+      locate(t, p, tl);
+      gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
       if (kb1 <= kb0) continue;
+      const EpiParams& ep = gp.ep[p];
+      const CUtensorMap* tmap_c = &gp.tc[p];
+      const CUtensorMap* tmap_x = &gp.taux[p];
       const int acc = local % NACC;
       const uint32_t acc_phase = (local / NACC) & 1u;
       ++local;
       const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's boxes
       const int n_base = n_blk * BN + half * SLICE;
       const bool live = m0 < (int)ep.M;                // a box entirely below the matrix is neither loaded nor stored
-      const bool add_bias = kBias && sp == 0;
+      const bool add_bias = kBias && sp == 0 && ep.bias != nullptr;
       if (kLoad && live && lane == 0 && n_base < (int)ep.N) {     // operand box of group 0: in flight while the MMAs of this tile still run
         mbar_expect_tx(aux_bar(ew), kTmaBox);
-        tma_load_2d(box1, &gp.taux, aux_bar(ew), n_base, m0);
+        tma_load_2d(box1, tmap_x, aux_bar(ew), n_base, m0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (kRowsum && n_blk == 0 && half == 0) {
+      if (kRowsum && ep.rowsum_out != nullptr && n_blk == 0 && half == 0) {
         const float rs = tmem_ld_32x32b_x1(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ROWSUM_COL + acc * 16));
         if (m0 + lane < (int)ep.M) atomicAdd(ep.rowsum_out + m0 + lane, rs);
       }
@@ -640,13 +643,13 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
         __syncwarp();                                  // (also: every lane has consumed the operand box)
         if (lane == 0) {
           if (active) {
-            if (kRed) tma_reduce_add_2d(&gp.tc, obox, n0, m0); else tma_store_2d(&gp.tc, obox, n0, m0);
-            if (kAux) tma_store_2d(&gp.taux, box1, n0, m0);
+            if (kRed) tma_reduce_add_2d(tmap_c, obox, n0, m0); else tma_store_2d(tmap_c, obox, n0, m0);
+            if (kAux) tma_store_2d(tmap_x, box1, n0, m0);
           }
           bulk_commit();
           if (kLoad && live && g + 1 < NGRP && n0 + GW < (int)ep.N) {     // next group's operand box
             mbar_expect_tx(aux_bar(ew), kTmaBox);
-            tma_load_2d(box1, &gp.taux, aux_bar(ew), n0 + GW, m0);
+            tma_load_2d(box1, tmap_x, aux_bar(ew), n0 + GW, m0);
           }
         }
       }
@@ -923,16 +926,16 @@ template <int BN, int STAGES_, bool AK, bool BKM, int EPI, int CG>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const TileSched& ts, const EpiParams& ep, cudaStream_t st) {
   GemmGroup<1> gp;
   gp.ta[0] = ta; gp.tb[0] = tb; gp.ep[0] = ep; gp.ts[0] = ts;
-  gp.tc = ta; gp.taux = ta;
+  gp.tc[0] = ta; gp.taux[0] = ta;
   if constexpr (direct_epi(EPI)) {           // epilogue tensors as [M][N] TMA tensors, box = 32 rows x 128 bytes
     constexpr bool kF32 = (EPI & EPI_BF16) == 0;
-    int rc = get_tensor_map(ep.out, ep.N, ep.M, ep.ldo, kF32 ? -32 : 32, &gp.tc);
+    int rc = get_tensor_map(ep.out, ep.N, ep.M, ep.ldo, kF32 ? -32 : 32, &gp.tc[0]);
     if (rc) return rc;
     if constexpr ((EPI & EPI_RES) != 0) {
-      rc = get_tensor_map(ep.res, ep.N, ep.M, ep.ldres, -32, &gp.taux);
+      rc = get_tensor_map(ep.res, ep.N, ep.M, ep.ldres, -32, &gp.taux[0]);
     } else if constexpr ((EPI & (EPI_AUX | EPI_DGELU)) != 0) {
       const void* aux = (EPI & EPI_AUX) ? (const void*)ep.aux_out : (const void*)ep.aux_in;
-      rc = get_tensor_map(aux, ep.N, ep.M, ep.ldaux, 32, &gp.taux);
+      rc = get_tensor_map(aux, ep.N, ep.M, ep.ldaux, 32, &gp.taux[0]);
     }
     if (rc) return rc;
   }
@@ -1098,21 +1101,43 @@ int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st) {
 int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) {
   GemmGroup<kMaxGroup> gp;
   memset(&gp, 0, sizeof(gp));
-  int64_t mn_total = 0;
-  for (int p = 0; p < count; ++p) mn_total += ((a[p].M + BM - 1) / BM) * ((a[p].N + 127) / 128);
+  const bool ak = a[0].a_kmajor != 0, bk = a[0].b_kmajor != 0;
+  // A group whose members all have one of the simple epilogues runs the compile-time (TMA) epilogue kernel:
+  //   forward  bias (or none) -> bf16      dgrad  -> bf16      wgrad  f32 reduce (+ row sums where requested)
+  int gmask = -2;
+  for (int p = 0; p < count; ++p) {
+    int em = epi_mask(a[p]);
+    if (em >= 0) {
+      if (em == EPI_BF16 && ak && bk) em = EPI_BIAS | EPI_BF16;            // bias pointer is checked at run time
+      if (em == EPI_RED) em = EPI_RED | EPI_ROWSUM;                          // rowsum_out pointer is checked at run time
+      const bool ok = (ak && bk && em == (EPI_BIAS | EPI_BF16)) || (ak && !bk && em == EPI_BF16) || (!ak && !bk && em == (EPI_RED | EPI_ROWSUM));
+      if (!ok) em = -1;
+    }
+    gmask = (gmask == -2 || gmask == em) ? em : -1;
+  }
+  // wgrad groups of large problems (a ViT block's Linears) use CTA-pair 256 x 256 tiles, everything else 128 x 128
+  int64_t pair_tiles = 0, mn_total = 0;
+  for (int p = 0; p < count; ++p) {
+    pair_tiles += ((a[p].M + 255) / 256) * ((a[p].N + 255) / 256);
+    mn_total += ((a[p].M + BM - 1) / BM) * ((a[p].N + 127) / 128);
+  }
+  bool pair = gmask == (EPI_RED | EPI_ROWSUM) && g_allow_2cta.load() && pair_tiles >= 8;
+  for (int p = 0; p < count && pair; ++p) pair = a[p].M >= 256 && a[p].N >= 256;
+  const int tm = pair ? 256 : 128, tn = pair ? 256 : 128;
+  const int64_t units = pair ? num_sms() / 2 : num_sms(), tiles_total = pair ? pair_tiles : mn_total;
   int end = 0, rc;
   for (int p = 0; p < kMaxGroup; ++p) {
     if (p >= count) {                 // unused slot: no tiles; keep valid (never dereferenced) descriptors
-      gp.ta[p] = gp.ta[0]; gp.tb[p] = gp.tb[0]; gp.ep[p] = gp.ep[0]; gp.ts[p] = gp.ts[0];
+      gp.ta[p] = gp.ta[0]; gp.tb[p] = gp.tb[0]; gp.tc[p] = gp.tc[0]; gp.taux[p] = gp.taux[0]; gp.ep[p] = gp.ep[0]; gp.ts[p] = gp.ts[0];
       gp.tile_end[p] = end;
       continue;
     }
     const davf_gemm_args& g = a[p];
     const int kb_total = (int)((g.K + BK - 1) / BK);
-    const int m_tiles = (int)((g.M + BM - 1) / BM), n_tiles = (int)((g.N + 127) / 128);
+    const int m_tiles = (int)((g.M + tm - 1) / tm), n_tiles = (int)((g.N + tn - 1) / tn);
     int splits = g.split_k > 0 ? g.split_k : 1;
-    if (g.split_k <= 0 && g.accumulate && mn_total < num_sms()) {
-      splits = (int)(num_sms() / mn_total);
+    if (g.split_k <= 0 && g.accumulate && tiles_total < units) {
+      splits = (int)(units / tiles_total);
       if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
     }
     if (splits > kb_total) splits = kb_total;
@@ -1128,10 +1153,20 @@ int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st) 
     if (rc) return rc;
     gp.ep[p] = make_epi(g);
     gp.ep[p].debug_clocks = nullptr;
+    gp.tc[p] = gp.ta[p]; gp.taux[p] = gp.ta[p];
+    if (gmask >= 0) {
+      rc = get_tensor_map(g.out, g.N, g.M, g.ldo, g.out_bf16 ? 32 : -32, &gp.tc[p]);
+      if (rc) return rc;
+    }
     end += m_tiles * n_tiles * splits;
     gp.tile_end[p] = end;
   }
-  const bool ak = a[0].a_kmajor != 0, bk = a[0].b_kmajor != 0;
+  if (gmask == (EPI_BIAS | EPI_BF16)) return launch_group<128, 6, true, true, EPI_BIAS | EPI_BF16, 1, kMaxGroup>(gp, st);
+  if (gmask == EPI_BF16) return launch_group<128, 6, true, false, EPI_BF16, 1, kMaxGroup>(gp, st);
+  if (gmask == (EPI_RED | EPI_ROWSUM)) {
+    if (pair) return launch_group<256, 6, false, false, EPI_RED | EPI_ROWSUM, 2, kMaxGroup>(gp, st);
+    return launch_group<128, 6, false, false, EPI_RED | EPI_ROWSUM, 1, kMaxGroup>(gp, st);
+  }
   if (ak && bk) return launch_group<128, 6, true, true, -1, 1, kMaxGroup>(gp, st);
   if (ak && !bk) return launch_group<128, 6, true, false, -1, 1, kMaxGroup>(gp, st);
   if (!ak && !bk) return launch_group<128, 6, false, false, -1, 1, kMaxGroup>(gp, st);

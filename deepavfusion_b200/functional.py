@@ -37,24 +37,36 @@ def linear_fwd(st: ParamStore, x: Tensor, W: nn.Parameter, b: Optional[nn.Parame
     return K.gemm(x, _w2d(st.lowp(W), cols), True, True, bias=None if b is None else b.data, **epi)
 
 
+def launch_wgrads(st: ParamStore, probs) -> None:
+    """probs = [((dy, x, False, False), kwargs)]: weight-gradient GEMMs (+ bias-gradient row sums) of one backward
+    region as ONE grouped launch.  Nothing in backward consumes dW / db, so the launch leaves the dgrad critical
+    path: it is issued on a dedicated stream that is joined only at the end of backward."""
+    if not probs:
+        return
+    ws = st.wgrad_stream()
+    if ws is None:
+        K.gemm_grouped(probs)
+        return
+    ws.wait_stream(torch.cuda.current_stream())
+    for (dy, x, _, _), _kw in probs:
+        dy.record_stream(ws)
+        x.record_stream(ws)
+    with torch.cuda.stream(ws):
+        K.gemm_grouped(probs)
+
+
 def linear_bwd(st: ParamStore, dy: Tensor, x: Tensor, W: nn.Parameter, b: Optional[nn.Parameter], cols=None,
-               need_dx: bool = True, **epi):
+               need_dx: bool = True, defer: Optional[list] = None, **epi):
     """Accumulates dW (+= dy^T x) and db (+= colsum dy) into the flat gradient buffer and returns
-    dx = dy W[:, cols] (with optional fused epilogue) or None."""
+    dx = dy W[:, cols] (with optional fused epilogue) or None.  With ``defer`` (a list) the wgrad problem is appended
+    to it instead of being launched: the caller groups a region's wgrads into one launch (``launch_wgrads``)."""
     want_b = b is not None and b.requires_grad
     if W.requires_grad:       # bias gradient rides along in the wgrad launch (ones-tile MMA)
-        ws = st.wgrad_stream()
-        if ws is None:
-            K.gemm(dy, x, False, False, out=_w2d(st.grad(W), cols), accumulate=True, rowsum_out=st.grad(b) if want_b else None)
+        prob = ((dy, x, False, False), dict(out=_w2d(st.grad(W), cols), accumulate=True, rowsum_out=st.grad(b) if want_b else None))
+        if defer is not None:
+            defer.append(prob)
         else:
-            # Nothing in backward consumes dW / db, so the wgrad launch leaves the dgrad critical path: it is
-            # issued on a dedicated stream that is joined only at the end of backward.
-            ws.wait_stream(torch.cuda.current_stream())
-            dy.record_stream(ws)
-            x.record_stream(ws)
-            gw, gb = _w2d(st.grad(W), cols), (st.grad(b) if want_b else None)
-            with torch.cuda.stream(ws):
-                K.gemm(dy, x, False, False, out=gw, accumulate=True, rowsum_out=gb)
+            launch_wgrads(st, [prob])
     elif want_b:
         K.colsum_bf16(dy, st.grad(b))
     if not need_dx:
@@ -193,7 +205,8 @@ class AttnBranchFn(torch.autograd.Function):
         S, H = nP + n, m.heads
         hd = D // H
         dyb = _lowp_grad(st, dy.view(B * n, D))
-        do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b)                # [B*n, D] bf16
+        wg = []                                                                       # proj + qkv wgrads: one grouped launch
+        do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b, defer=wg)      # [B*n, D] bf16
         dqkv = torch.empty_like(qkv)
         d5 = dqkv.view(B, S, 3, H, hd)
         if nP:
@@ -201,7 +214,8 @@ class AttnBranchFn(torch.autograd.Function):
         q5 = qkv.view(B, S, 3, H, hd)
         K.attention_bwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], do.view(B, n, H, hd), lse, hd ** -0.5,
                         d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2], o=o)
-        dxn = linear_bwd(st, dqkv, xn, m.qkv_w, m.qkv_b)                              # [B*S, D] bf16
+        dxn = linear_bwd(st, dqkv, xn, m.qkv_w, m.qkv_b, defer=wg)                    # [B*S, D] bf16
+        launch_wgrads(st, wg)
         gw, gb = st.grad(m.norm_w), st.grad(m.norm_b)
         if nP:
             dxp, dx = K.layernorm_bwd(x0, x1, m.norm_w.data, mean, rstd, dxn, None, None, dy, gw, gb,
@@ -240,8 +254,10 @@ class MlpBranchFn(torch.autograd.Function):
         dy = dy.contiguous()
         D = dy.shape[-1]
         dyb = _lowp_grad(st, dy.view(-1, D))
-        dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, act=K.ACT_DGELU, aux_in=h)      # dgrad times the saved gelu'
-        dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b)
+        wg = []                                                                       # fc2 + fc1 wgrads: one grouped launch
+        dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, defer=wg, act=K.ACT_DGELU, aux_in=h)   # dgrad times the saved gelu'
+        dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b, defer=wg)
+        launch_wgrads(st, wg)
         lp = _new_lowp(dy)                                                            # consumed by the attention branch's backward
         dx, _ = K.layernorm_bwd(x2, None, m.norm_w.data, mean, rstd, dxn, None, dy.view(1, -1, D), None,
                                 st.grad(m.norm_w), st.grad(m.norm_b), dx0_lowp=lp)

@@ -213,6 +213,11 @@ def group_case(tag, shapes, ak, bk, mode):
                 res = rnd(M // 8 * F_, N, seed=330)
                 kw.update(res=res, out=torch.zeros(M // 8 * F_, N, device='cuda'), window=(8, F_, 16), want_aux=True)
                 ekw.update(res=res.cpu(), out=torch.zeros(M // 8 * F_, N), window=(8, F_, 16), want_aux=True)
+        elif mode == 'fwd_static':
+            if j != 1:
+                bias = rnd(N, seed=320 + j); kw['bias'] = bias; ekw['bias'] = bias.cpu()
+        elif mode == 'dgrad_static':
+            pass
         elif mode == 'dgrad':
             if j == 0:
                 res = rnd(M, N, seed=331); kw.update(res=res, out_dtype=torch.float32); ekw.update(res=res.cpu(), out_dtype=torch.float32)
@@ -232,6 +237,11 @@ def group_case(tag, shapes, ak, bk, mode):
             check(f'{{tag}}[{{j}}]', g, e, **tol)
         if 'rowsum_out' in probs[j][1]:
             check(f'{{tag}}[{{j}}] rowsum', probs[j][1]['rowsum_out'], ekw['rowsum_out'], 1e-2, 1e-1 * (Kd / 768) ** 0.5)
+# groups that qualify for the compile-time (TMA) epilogue kernels: bias-or-none forward, plain dgrad, wgrad as CTA pairs
+group_case('group fwd static', [(512, 768, 768), (3136, 1536, 768), (512, 768, 768), (1216, 1536, 768), (1024, 192, 768)], True, True, 'fwd_static')
+group_case('group dgrad static', [(512, 768, 768), (512, 768, 768), (3136, 768, 1536), (1216, 768, 1536)], True, False, 'dgrad_static')
+group_case('group wgrad pairs', [(768, 768, 3136), (2304, 768, 5184)], False, False, 'wgrad')
+group_case('group wgrad pairs mlp', [(768, 3072, 3136), (3072, 768, 3136)], False, False, 'wgrad')
 group_case('group fwd', [(512, 768, 768), (512, 768, 768), (3136, 1536, 768), (1216, 1536, 768), (512, 192, 768)], True, True, 'fwd')
 group_case('group dgrad', [(512, 768, 960), (512, 768, 960), (40, 768, 192)], True, False, 'dgrad')
 group_case('group wgrad', [(768, 768, 512), (1536, 768, 3136), (192, 768, 512), (768, 768, 512), (960, 768, 512), (768, 768, 1216), (768, 72, 512)], False, False, 'wgrad')

@@ -1,0 +1,13 @@
+import os, sys
+sys.path.insert(0, "/root/repo")
+import torch
+import deepavfusion_b200.kernels as K
+bf16 = torch.bfloat16
+def r(*s, dt=bf16): return (torch.randn(*s, device="cuda") * 0.05).to(dt)
+# wgrad qkv image: dW[2304,768] += dy[5184,2304]^T x[5184,768]  (+ bias grad)
+dy, x = r(5184, 2304), r(5184, 768)
+out = torch.zeros(2304, 768, device="cuda"); db = torch.zeros(2304, device="cuda")
+for _ in range(3):
+    K.gemm(dy, x, False, False, out=out, accumulate=True, rowsum_out=db)
+torch.cuda.synchronize()
+print("done")
