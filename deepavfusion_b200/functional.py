@@ -320,25 +320,19 @@ def group_fwd(items):
     return K.gemm_grouped([((x, l.w, True, True), dict(bias=l.b, **kw)) for x, l, kw in items])
 
 
-def group_bwd(st: ParamStore, items):
-    """items = [(dy, x, _Lin, dgrad epilogue kwargs or None)]: the wgrad (+ bias gradient) launches of all items
-    go out as one grouped launch on the wgrad stream, the dgrad launches as one grouped launch on the
-    current stream.  Returns the dx list (None where no dgrad was requested)."""
+def group_bwd(st: ParamStore, items, defer: Optional[list] = None):
+    """items = [(dy, x, _Lin, dgrad epilogue kwargs or None)]: the dgrad launches go out as one grouped launch on the
+    current stream; the wgrad (+ bias gradient) problems are appended to ``defer`` (flushed by the caller with
+    ``launch_wgrads`` before the region reports its parameters done) or, without it, launched as one group on the
+    wgrad stream.  Returns the dx list (None where no dgrad was requested)."""
     wg = [((dy, x, False, False), dict(out=l.gw, accumulate=True, rowsum_out=l.gb)) for dy, x, l, _ in items if l.gw is not None]
     for dy, x, l, _ in items:
         if l.gw is None and l.gb is not None:
             K.colsum_bf16(dy, l.gb)
-    if wg:
-        ws = st.wgrad_stream()
-        if ws is None:
-            K.gemm_grouped(wg)
-        else:
-            ws.wait_stream(torch.cuda.current_stream())
-            for (dy, x, _, _), _kw in wg:
-                dy.record_stream(ws)
-                x.record_stream(ws)
-            with torch.cuda.stream(ws):
-                K.gemm_grouped(wg)
+    if defer is not None:
+        defer.extend(wg)
+    else:
+        launch_wgrads(st, wg)
     dg = [(i, ((dy, l.w, True, False), kw)) for i, (dy, x, l, kw) in enumerate(items) if kw is not None]
     out = [None] * len(items)
     for (i, _), r in zip(dg, K.gemm_grouped([c for _, c in dg])):
@@ -456,7 +450,8 @@ class FusionAttnFn(torch.autograd.Function):
 
         # ---- pair attention ----
         dr2 = K.cast_rows_bf16(d2, B * nmm, nmm, F, 0)
-        (do2,) = group_bwd(st, [(dr2, o2, L.proj, {})])
+        wg = []                                      # the block's ten wgrads leave in two grouped launches at the end
+        (do2,) = group_bwd(st, [(dr2, o2, L.proj, {})], wg)
         do2 = do2.view(B, nmm, H, hd)
         dq2 = torch.empty_like(q2)
         dkv2v, dkv2a = torch.empty_like(kv2v), torch.empty_like(kv2a)
@@ -474,10 +469,10 @@ class FusionAttnFn(torch.autograd.Function):
         idx_a = FusionAttnFn._idx(m, B, F, nmm + nv, na, dout.device)
         _, dpv, dpa = group_bwd(st, [(dq2, m2, L.q2, dict(out=dm2)),
                                      (dkv2v, pv, L.pair_v, dict(res=d2, res_idx=idx_v)),
-                                     (dkv2a, pa, L.pair_a, dict(res=d2, res_idx=idx_a))])
+                                     (dkv2a, pa, L.pair_a, dict(res=d2, res_idx=idx_a))], wg)
 
         # ---- the two cross attentions ----
-        do_v, do_a = group_bwd(st, [(dpv, ov.view(B * nv, D), L.proj_v, {}), (dpa, oa.view(B * na, D), L.proj_a, {})])
+        do_v, do_a = group_bwd(st, [(dpv, ov.view(B * nv, D), L.proj_v, {}), (dpa, oa.view(B * na, D), L.proj_a, {})], wg)
         dqv, dkvv, dqa, dkva = torch.empty_like(qv), torch.empty_like(kvv), torch.empty_like(qa), torch.empty_like(kva)
         kvv5, dkvv5 = kvv.view(B, Nv, 2, H, hd), dkvv.view(B, Nv, 2, H, hd)
         kva5, dkva5 = kva.view(B, Na, 2, H, hd), dkva.view(B, Na, 2, H, hd)
@@ -486,7 +481,8 @@ class FusionAttnFn(torch.autograd.Function):
         K.attention_bwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], do_a.view(B, na, H, hd), lse_a, scale,
                         dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1], o=oa.view(B, na, H, hd))
         _, _, dxv_n, dxa_n = group_bwd(st, [(dqv, mv, L.q_v, dict(out=dmv)), (dqa, ma, L.q_a, dict(out=dma)),
-                                            (dkvv, xv_n, L.kv_v, {}), (dkva, xa_n, L.kv_a, {})])
+                                            (dkvv, xv_n, L.kv_v, {}), (dkva, xa_n, L.kv_a, {})], wg)
+        launch_wgrads(st, wg)
 
         dxv, _ = K.layernorm_bwd(xv, None, m.n_img_w.data, mean_v, rstd_v, dxv_n, None, None, None,
                                  st.grad(m.n_img_w), st.grad(m.n_img_b))
