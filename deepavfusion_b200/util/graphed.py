@@ -73,9 +73,32 @@ class GraphedTrainStep:
         tr.accums = 0
 
     def __call__(self, image: torch.Tensor, audio: torch.Tensor):
-        """image / audio may live on the host (pinned): the copies run on the current stream before the replay."""
-        self.image.copy_(image, non_blocking=True)
-        self.audio.copy_(audio, non_blocking=True)
+        """image / audio may live on the host (pinned).  Host inputs travel on a dedicated copy stream into one of two
+        staging buffers and reach the graph's static input with a device-to-device copy, so the 45 MB H2D transfer of
+        step t+1 (~0.9 ms over PCIe) overlaps the compute of step t whenever the host runs ahead of the GPU."""
+        if image.device.type == "cpu" and audio.device.type == "cpu":
+            cur = torch.cuda.current_stream()
+            if not hasattr(self, "_cstream"):
+                self._cstream = torch.cuda.Stream()
+                self._stage = [(torch.empty_like(self.image), torch.empty_like(self.audio)) for _ in range(2)]
+                self._stage_free = [None, None]
+                self._k = 0
+            k = self._k
+            self._k ^= 1
+            si, sa = self._stage[k]
+            if self._stage_free[k] is not None:
+                self._cstream.wait_event(self._stage_free[k])       # the D2D copy that last read this staging slot
+            with torch.cuda.stream(self._cstream):
+                si.copy_(image, non_blocking=True)
+                sa.copy_(audio, non_blocking=True)
+                ready = self._cstream.record_event()
+            cur.wait_event(ready)
+            self.image.copy_(si, non_blocking=True)
+            self.audio.copy_(sa, non_blocking=True)
+            self._stage_free[k] = cur.record_event()
+        else:
+            self.image.copy_(image, non_blocking=True)
+            self.audio.copy_(audio, non_blocking=True)
         self.trainer.optimizer._sync_hp()
         self.graph.replay()
         if self.distributed and not self.overlap_comm:
@@ -85,3 +108,33 @@ class GraphedTrainStep:
             self.trainer.optimizer.n_steps += 1
         self.trainer.n_steps += 1
         return self.loss_image, self.loss_audio, self.grad_norm
+
+    # -- pipelined host read-back -------------------------------------------------------------------------
+    def step_async(self, image: torch.Tensor, audio: torch.Tensor) -> None:
+        """One step whose (loss_image, loss_audio, grad_norm) are copied to pinned host memory asynchronously, to be
+        collected with ``pop_metrics``.  A training loop that logs step t's loss after it has launched step t+1
+        (train.py:166 reads ``loss.item()`` for the meters only) never drains the GPU: the host-side graph launch
+        of the next step (~0.7 ms for ~1,100 kernel nodes) overlaps the current step instead of following it."""
+        if not hasattr(self, "_ring"):
+            self._ring = [(torch.empty(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._dev3 = torch.empty(3, dtype=torch.float32, device=self.image.device)
+            self._head = self._tail = 0
+        assert self._head - self._tail < len(self._ring), "pop_metrics() must be called to drain the ring"
+        li, la, norm = self(image, audio)
+        torch.stack((li.reshape(()), la.reshape(()), norm.reshape(())), out=self._dev3)
+        host, ev = self._ring[self._head % len(self._ring)]
+        host.copy_(self._dev3, non_blocking=True)
+        ev.record()
+        self._head += 1
+
+    def pending(self) -> int:
+        return getattr(self, "_head", 0) - getattr(self, "_tail", 0)
+
+    def pop_metrics(self):
+        """(loss_image, loss_audio, grad_norm) of the oldest step not yet collected, as Python floats; waits for that
+        step only."""
+        assert self.pending() > 0
+        host, ev = self._ring[self._tail % len(self._ring)]
+        ev.synchronize()
+        self._tail += 1
+        return float(host[0]), float(host[1]), float(host[2])
