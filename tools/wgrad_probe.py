@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""One representative wgrad launch (image-block qkv: dW[2304,768] += dy^T x, K = 5184 rows, + bias-gradient row sums)
+for `ncu --set full -k regex:gemm_tc -s 2 -c 1 python tools/wgrad_probe.py`."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import deepavfusion_b200.kernels as K
 bf16 = torch.bfloat16
