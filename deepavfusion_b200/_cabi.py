@@ -113,6 +113,8 @@ SIGNATURES = {
     "davf_batchnorm1d_bwd": (i, [vp, vp, vp, vp, i, i, i, vp, vp]),
     "davf_head_fwd": (i, [vp, vp, vp, i, i, i, vp, vp]),
     "davf_head_bwd": (i, [vp, vp, vp, i, i, i, vp, vp, vp, vp]),
+    "davf_scale_rows_add": (i, [vp, vp, vp, i, i64, i, vp, vp]),
+    "davf_scale_rows": (i, [vp, vp, i, i64, i, vp, vp, vp]),
 }
 
 _lib = None

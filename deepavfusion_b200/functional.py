@@ -88,6 +88,13 @@ def _new_lowp(like: Tensor) -> Tensor:
     return torch.empty(like.numel() // like.shape[-1], like.shape[-1], dtype=torch.bfloat16, device=like.device)
 
 
+def droppath_scale(B: int, drop_prob: float, device) -> Tensor:
+    """Per-sample keep-mask / keep_prob of timm DropPath (scale_by_keep=True).  The RNG draw cannot reproduce the
+    reference's ``bernoulli_`` stream bit for bit (parity runs use drop_path = 0 or inject the masks)."""
+    keep = 1.0 - drop_prob
+    return (torch.rand(B, device=device) < keep).to(torch.float32) / keep
+
+
 def params_of(ns: SimpleNamespace):
     """All nn.Parameters referenced by a region namespace (nested namespaces included)."""
     out = []
@@ -172,7 +179,8 @@ class AttnBranchFn(torch.autograd.Function):
     MLP work is done for them."""
 
     @staticmethod
-    def forward(ctx, xp: Optional[Tensor], x: Tensor, anchor: Tensor, m: SimpleNamespace):
+    def forward(ctx, xp: Optional[Tensor], x: Tensor, anchor: Tensor, m: SimpleNamespace, drop: Optional[Tensor] = None):
+        """``drop``: per-sample DropPath scale [B] of this residual branch (None: no stochastic depth)."""
         st: ParamStore = m.store
         B, n, D = x.shape
         x = x.contiguous()
@@ -190,8 +198,11 @@ class AttnBranchFn(torch.autograd.Function):
         qkv = linear_fwd(st, xn, m.qkv_w, m.qkv_b)                                    # [B*S, 3D] bf16
         q5 = qkv.view(B, S, 3, H, hd)
         o, lse = K.attention_fwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], hd ** -0.5)  # [B,n,H,hd]
-        y = linear_fwd(st, o.view(B * n, D), m.proj_w, m.proj_b, res=x.view(B * n, D), out_dtype=torch.float32)
-        ctx.m, ctx.nP = m, nP
+        if drop is None:
+            y = linear_fwd(st, o.view(B * n, D), m.proj_w, m.proj_b, res=x.view(B * n, D), out_dtype=torch.float32)
+        else:
+            y = K.scale_rows_add(x.view(B * n, D), linear_fwd(st, o.view(B * n, D), m.proj_w, m.proj_b, out_dtype=torch.float32), drop, n)
+        ctx.m, ctx.nP, ctx.drop = m, nP, drop
         ctx.save_for_backward(x0, x1, mean, rstd, xn, qkv, o, lse)
         return y.view(B, n, D)
 
@@ -204,7 +215,7 @@ class AttnBranchFn(torch.autograd.Function):
         B, n, D = dy.shape
         S, H = nP + n, m.heads
         hd = D // H
-        dyb = _lowp_grad(st, dy.view(B * n, D))
+        dyb = _lowp_grad(st, dy.view(B * n, D)) if ctx.drop is None else K.scale_rows(dy.view(B * n, D), ctx.drop, n)[1]
         wg = []                                                                       # proj + qkv wgrads: one grouped launch
         do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b, defer=wg)      # [B*n, D] bf16
         dqkv = torch.empty_like(qkv)
@@ -226,7 +237,7 @@ class AttnBranchFn(torch.autograd.Function):
             st.stash_lowp_grad(dx, lp)
             dxp = None
         _done(m)
-        return dxp, dx, None, None
+        return dxp, dx, None, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -234,15 +245,18 @@ class AttnBranchFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 class MlpBranchFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x: Tensor, anchor: Tensor, m: SimpleNamespace):
+    def forward(ctx, x: Tensor, anchor: Tensor, m: SimpleNamespace, drop: Optional[Tensor] = None):
         st: ParamStore = m.store
         x = x.contiguous()
         D = x.shape[-1]
         x2 = x.view(1, -1, D)
         xn, _, mean, rstd = K.layernorm_fwd(x2, None, m.norm_w.data, m.norm_b.data, m.eps)
         a, h = linear_fwd(st, xn, m.fc1_w, m.fc1_b, act=K.ACT_GELU, want_aux=True)   # a = gelu(z), h = gelu'(z) (bf16), z = fc1 output
-        y = linear_fwd(st, a, m.fc2_w, m.fc2_b, res=x2.view(-1, D), out_dtype=torch.float32)
-        ctx.m = m
+        if drop is None:
+            y = linear_fwd(st, a, m.fc2_w, m.fc2_b, res=x2.view(-1, D), out_dtype=torch.float32)
+        else:                                                                         # DropPath: x + scale[b] * branch
+            y = K.scale_rows_add(x2.view(-1, D), linear_fwd(st, a, m.fc2_w, m.fc2_b, out_dtype=torch.float32), drop, x.shape[1])
+        ctx.m, ctx.drop, ctx.rps = m, drop, x.shape[1]
         ctx.save_for_backward(x2, mean, rstd, xn, h, a)
         return y.view(x.shape)
 
@@ -253,7 +267,7 @@ class MlpBranchFn(torch.autograd.Function):
         x2, mean, rstd, xn, h, a = ctx.saved_tensors
         dy = dy.contiguous()
         D = dy.shape[-1]
-        dyb = _lowp_grad(st, dy.view(-1, D))
+        dyb = _lowp_grad(st, dy.view(-1, D)) if ctx.drop is None else K.scale_rows(dy.view(-1, D), ctx.drop, ctx.rps)[1]
         wg = []                                                                       # fc2 + fc1 wgrads: one grouped launch
         dh = linear_bwd(st, dyb, a, m.fc2_w, m.fc2_b, defer=wg, act=K.ACT_DGELU, aux_in=h)   # dgrad times the saved gelu'
         dxn = linear_bwd(st, dh, xn, m.fc1_w, m.fc1_b, defer=wg)
@@ -264,7 +278,7 @@ class MlpBranchFn(torch.autograd.Function):
         dx = dx.view(dy.shape)
         st.stash_lowp_grad(dx, lp)
         _done(m)
-        return dx, None, None
+        return dx, None, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -384,7 +398,7 @@ class FusionAttnFn(torch.autograd.Function):
             q2=_lin_of(st, m.q_w, m.q_b), pair_v=pair_v, pair_a=pair_a, proj=_lin_of(st, m.proj_w, m.proj_b))
 
     @staticmethod
-    def forward(ctx, xmm: Tensor, xv: Tensor, xa: Tensor, anchor: Tensor, m: SimpleNamespace):
+    def forward(ctx, xmm: Tensor, xv: Tensor, xa: Tensor, anchor: Tensor, m: SimpleNamespace, drop: Optional[Tensor] = None):
         xmm, xv, xa = xmm.contiguous(), xv.contiguous(), xa.contiguous()
         B, F, D = xmm.shape
         nmm, nv, na = m.tkns
@@ -400,6 +414,7 @@ class FusionAttnFn(torch.autograd.Function):
         xv_n, _, mean_v, rstd_v = K.layernorm_fwd(xv, None, m.n_img_w.data, m.n_img_b.data, m.eps)
         xa_n, _, mean_a, rstd_a = K.layernorm_fwd(xa, None, m.n_aud_w.data, m.n_aud_b.data, m.eps)
         out = torch.empty(B * F, D, dtype=torch.float32, device=xmm.device)
+        res = mm_f if drop is None else None        # DropPath: the three projections land in `out` alone, the residual is added scaled
         Nv, Na = xv_n.shape[0] // B, xa_n.shape[0] // B
 
         # every Linear that only needs the normed inputs: CrossAttention q / kv of both modalities (:46-52) + pair q (:252)
@@ -409,8 +424,8 @@ class FusionAttnFn(torch.autograd.Function):
         oa, lse_a = K.attention_fwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], scale)
         # out[b, off:off+n] = LN_mm(xmm)[b, off:...] + proj(.) ; the bf16 proj outputs feed the pair attention
         (_, pv), (_, pa) = group_fwd([
-            (ov.view(B * nv, D), L.proj_v, dict(want_aux=True, res=mm_f, out=out, window=(nv, F, nmm))),
-            (oa.view(B * na, D), L.proj_a, dict(want_aux=True, res=mm_f, out=out, window=(na, F, nmm + nv)))])
+            (ov.view(B * nv, D), L.proj_v, dict(want_aux=True, res=res, out=out, window=(nv, F, nmm))),
+            (oa.view(B * na, D), L.proj_a, dict(want_aux=True, res=res, out=out, window=(na, F, nmm + nv)))])
         # factorised pair attention: [k | v] of each side in one GEMM against the stacked weight
         kv2v, kv2a = group_fwd([(pv, L.pair_v, {}), (pa, L.pair_a, {})])            # [B*nv, qk + D], [B*na, qk + D]
         q2v = q2.view(B, nmm, H, dq)
@@ -419,8 +434,10 @@ class FusionAttnFn(torch.autograd.Function):
         o2, lse2v = K.attention_fwd(q2v, k_v, v_v, scale)
         _, lse2a = K.attention_fwd(q2v, k_a, v_a, scale, out=o2, accumulate=True)
         o2 = o2.view(B * nmm, D)
-        K.gemm(o2, L.proj.w, bias=L.proj.b, res=mm_f, out=out, window=(nmm, F, 0))
-        ctx.m = m
+        K.gemm(o2, L.proj.w, bias=L.proj.b, res=res, out=out, window=(nmm, F, 0))
+        if drop is not None:                         # xmm + drop_path(res_fusion), fusion_blocks.py:283
+            out = K.scale_rows_add(mm_f, out, drop, F)
+        ctx.m, ctx.drop = m, drop
         ctx.save_for_backward(xmm, xv, xa, mean_m, rstd_m, mean_v, rstd_v, mean_a, rstd_a, mm_b, xv_n, xa_n,
                               qv, kvv, ov, lse_v, pv, qa, kva, oa, lse_a, pa,
                               q2, kv2v, kv2a, lse2v, lse2a, o2)
@@ -443,7 +460,8 @@ class FusionAttnFn(torch.autograd.Function):
         scale = hd ** -0.5
         L = FusionAttnFn._lins(m)
         Nv, Na = xv_n.shape[0] // B, xa_n.shape[0] // B
-        d2 = dout.view(B * F, D)
+        d_res = dout.view(B * F, D)                                                 # gradient of the residual path (unscaled)
+        d2 = d_res if ctx.drop is None else K.scale_rows(d_res, ctx.drop, F, want_f32=True, want_bf16=False)[0]   # of the branch
         m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
         dseg = torch.empty_like(mm_b)                                               # d LN_mm(xmm), segment-major bf16
         dm2, dmv, dma = dseg[:B * nmm], dseg[B * nmm:B * (nmm + nv)], dseg[B * (nmm + nv):]
@@ -489,10 +507,10 @@ class FusionAttnFn(torch.autograd.Function):
         dxa, _ = K.layernorm_bwd(xa, None, m.n_aud_w.data, mean_a, rstd_a, dxa_n, None, None, None,
                                  st.grad(m.n_aud_w), st.grad(m.n_aud_b))
         seg = [0, nmm, nmm + nv, F]
-        dxmm, _ = K.layernorm_bwd(xmm, None, m.n_mm_w.data, mean_m, rstd_m, dseg, d2, None, None,
+        dxmm, _ = K.layernorm_bwd(xmm, None, m.n_mm_w.data, mean_m, rstd_m, dseg, d_res, None, None,
                                   st.grad(m.n_mm_w), st.grad(m.n_mm_b), seg_start=seg)
         _done(m)
-        return dxmm, dxv, dxa, None, None
+        return dxmm, dxv, dxa, None, None, None
 
 
 # --------------------------------------------------------------------------------------------

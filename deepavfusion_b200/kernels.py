@@ -484,6 +484,32 @@ def head_bwd(dy: Tensor, x: Tensor, W: Tensor, dW: Optional[Tensor], db: Optiona
     return dx
 
 
+# --------------------------------------------------------------------------------------------
+# stochastic depth (fine-tuning only)
+# --------------------------------------------------------------------------------------------
+def scale_rows_add(res: Tensor, y: Tensor, scale: Tensor, rows_per_sample: int) -> Tensor:
+    """res + scale[sample] * y, f32 [rows, D] (rows sample-major)."""
+    _need(res, torch.float32, "res"); _need(y, torch.float32, "y"); _need(scale, torch.float32, "scale")
+    D = res.shape[-1]
+    rows = res.numel() // D
+    assert y.numel() == res.numel() and scale.numel() * rows_per_sample == rows
+    out = torch.empty_like(res)
+    check(_cabi.lib().davf_scale_rows_add(_ptr(res), _ptr(y), _ptr(scale), rows_per_sample, rows, D, _ptr(out), _stream()), "davf_scale_rows_add")
+    return out
+
+
+def scale_rows(src: Tensor, scale: Tensor, rows_per_sample: int, want_f32: bool = False, want_bf16: bool = True):
+    """scale[sample] * src as (f32 or None, bf16 or None), both [rows, D]."""
+    _need(src, torch.float32, "src"); _need(scale, torch.float32, "scale")
+    D = src.shape[-1]
+    rows = src.numel() // D
+    assert scale.numel() * rows_per_sample == rows
+    f = torch.empty(rows, D, dtype=torch.float32, device=src.device) if want_f32 else None
+    b = torch.empty(rows, D, dtype=torch.bfloat16, device=src.device) if want_bf16 else None
+    check(_cabi.lib().davf_scale_rows(_ptr(src), _ptr(scale), rows_per_sample, rows, D, _ptr(f), _ptr(b), _stream()), "davf_scale_rows")
+    return f, b
+
+
 def set_gemm_sms(n: int) -> int:
     """SMs the persistent GEMM grids use (see davf_set_gemm_sms); returns the value in effect."""
     return int(_cabi.lib().davf_set_gemm_sms(int(n)))

@@ -61,8 +61,9 @@ class FusionBlock_FactorizedAVInteractions(nn.Module):
     def __init__(self, dim, num_heads, attn_ratio=0.25, mlp_ratio=4.0, qkv_bias=False, fusion_tkns=(8, 4, 4),
                  drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm):
         super().__init__()
-        _no_dropout(drop=drop, attn_drop=attn_drop, drop_path=drop_path)
+        _no_dropout(drop=drop, attn_drop=attn_drop)
         assert act_layer is nn.GELU
+        self.drop_path = float(drop_path)          # fusion_blocks.py:276: one DropPath module, two independent draws (:283,:288)
         self.norm1_mm = norm_layer(dim)
         self.norm1_aud = norm_layer(dim)
         self.norm1_img = norm_layer(dim)
@@ -90,5 +91,9 @@ class FusionBlock_FactorizedAVInteractions(nn.Module):
         if return_attention:
             raise NotImplementedError("return_attention is a visualisation path, not on the training hot path")
         a, f = self._ns
-        xmm = Fn.FusionAttnFn.apply(xmm, xv, xa, a.n_mm_w, a)
-        return Fn.MlpBranchFn.apply(xmm, f.norm_w, f)
+        d1 = d2 = None
+        if self.drop_path > 0.0 and self.training:
+            d1 = Fn.droppath_scale(xmm.shape[0], self.drop_path, xmm.device)
+            d2 = Fn.droppath_scale(xmm.shape[0], self.drop_path, xmm.device)
+        xmm = Fn.FusionAttnFn.apply(xmm, xv, xa, a.n_mm_w, a, d1)
+        return Fn.MlpBranchFn.apply(xmm, f.norm_w, f, d2)

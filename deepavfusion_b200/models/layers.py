@@ -26,8 +26,7 @@ def _no_dropout(**kw):
     for k, v in kw.items():
         if v:
             raise NotImplementedError(
-                f"{k}={v}: stochastic depth / dropout are not on the pre-training hot path "
-                "(all reference pre-training configs use 0); only 0 is implemented")
+                f"{k}={v}: dropout is not on the hot path (every reference config uses 0); only 0 is implemented")
 
 
 class PatchEmbed(nn.Module):
@@ -71,7 +70,8 @@ class Block(nn.Module):
                  drop_path=0.0, attn_drop=0.0, proj_drop=0.0):
         super().__init__()
         assert qkv_bias, "qkv_bias=False is not used by the reference"
-        _no_dropout(drop_path=drop_path, attn_drop=attn_drop, proj_drop=proj_drop)
+        _no_dropout(attn_drop=attn_drop, proj_drop=proj_drop)
+        self.drop_path = float(drop_path)          # timm Block.drop_path1 / drop_path2 (same rate, independent draws)
         self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, num_heads)
         self.norm2 = norm_layer(dim)
@@ -90,8 +90,12 @@ class Block(nn.Module):
 
     def forward(self, x: torch.Tensor, prefix: Optional[torch.Tensor] = None) -> torch.Tensor:
         a, f = self._ns
-        x = Fn.AttnBranchFn.apply(prefix, x, a.norm_w, a)
-        return Fn.MlpBranchFn.apply(x, f.norm_w, f)
+        d1 = d2 = None
+        if self.drop_path > 0.0 and self.training:      # stochastic depth: one per-sample draw per residual branch
+            d1 = Fn.droppath_scale(x.shape[0], self.drop_path, x.device)
+            d2 = Fn.droppath_scale(x.shape[0], self.drop_path, x.device)
+        x = Fn.AttnBranchFn.apply(prefix, x, a.norm_w, a, d1)
+        return Fn.MlpBranchFn.apply(x, f.norm_w, f, d2)
 
 
 class FinalNorm(nn.LayerNorm):

@@ -276,6 +276,16 @@ int davf_head_fwd(const float* x, const float* W, const float* bias, int B, int 
 int davf_head_bwd(const float* dy, const float* x, const float* W, int B, int C, int D, float* dW, float* db, float* dx,
                   davf_stream_t s);
 
+/* ---- stochastic depth (timm DropPath on the residual branches; models/vits.py:33, models/fusion_blocks.py:276,283,288;
+ * only configs/finetune.yaml:36 sets drop_path > 0) --------------------------------------------------------------
+ * scale f32 [B] = keep-mask / keep_prob per sample; rows are sample-major with rows_per_sample rows each.
+ *   davf_scale_rows_add: out = res + scale[r / rows_per_sample] * y          (f32 [rows, D]; the residual add of a dropped branch)
+ *   davf_scale_rows    : dst = scale[r / rows_per_sample] * src  as f32 and / or bf16 (either may be NULL): the branch gradient */
+int davf_scale_rows_add(const float* res, const float* y, const float* scale, int rows_per_sample, int64_t rows, int D,
+                        float* out, davf_stream_t s);
+int davf_scale_rows(const float* src, const float* scale, int rows_per_sample, int64_t rows, int D, float* dst_f32,
+                    davf_bf16* dst_bf16, davf_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,11 +287,20 @@ def _mlp(P: _Prec, sd, pre: str, x: Tensor) -> Tensor:
     return P.linear(F.gelu(h), sd[f"{pre}.fc2.weight"], sd[f"{pre}.fc2.bias"])
 
 
-def vit_block(P: _Prec, sd, pre: str, x: Tensor, heads: int, eps: float) -> Tensor:
-    """timm Block.forward with ls*/drop_path* = Identity:
-    x = x + attn(norm1(x)); x = x + mlp(norm2(x))."""
-    x = x + _attention(P, sd, f"{pre}.attn", P.layer_norm(x, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], eps), heads)
-    x = x + _mlp(P, sd, f"{pre}.mlp", P.layer_norm(x, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], eps))
+def _dp(drops, x: Tensor) -> Tensor:
+    """timm DropPath (layers/drop.py): x * keep_mask / keep_prob with one value per sample.  ``drops`` is None
+    (Identity) or an iterator of per-sample scale vectors [B], consumed in the reference's call order."""
+    if drops is None:
+        return x
+    s = next(drops)
+    return x * s.view(-1, *([1] * (x.dim() - 1))).to(x.dtype)
+
+
+def vit_block(P: _Prec, sd, pre: str, x: Tensor, heads: int, eps: float, drops=None) -> Tensor:
+    """timm Block.forward with ls* = Identity:
+    x = x + drop_path1(attn(norm1(x))); x = x + drop_path2(mlp(norm2(x)))."""
+    x = x + _dp(drops, _attention(P, sd, f"{pre}.attn", P.layer_norm(x, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], eps), heads))
+    x = x + _dp(drops, _mlp(P, sd, f"{pre}.mlp", P.layer_norm(x, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], eps)))
     return x
 
 
@@ -331,14 +340,14 @@ def _factorized_attention(P: _Prec, sd, pre: str, xmm: Tensor, xv: Tensor, xa: T
     return torch.cat((o, xmm_v, xmm_a), dim=1)                             # :262
 
 
-def fusion_block(P: _Prec, sd, pre: str, xmm: Tensor, xv: Tensor, xa: Tensor, cfg: OracleConfig) -> Tensor:
+def fusion_block(P: _Prec, sd, pre: str, xmm: Tensor, xv: Tensor, xa: Tensor, cfg: OracleConfig, drops=None) -> Tensor:
     """fusion_blocks.py:280-289.  The residual is taken from the *normed* fusion tokens (:281-283)."""
     e = cfg.fusion_eps
     xmm = P.layer_norm(xmm, sd[f"{pre}.norm1_mm.weight"], sd[f"{pre}.norm1_mm.bias"], e)
     xv = P.layer_norm(xv, sd[f"{pre}.norm1_img.weight"], sd[f"{pre}.norm1_img.bias"], e)
     xa = P.layer_norm(xa, sd[f"{pre}.norm1_aud.weight"], sd[f"{pre}.norm1_aud.bias"], e)
-    xmm = xmm + _factorized_attention(P, sd, f"{pre}.attn", xmm, xv, xa, cfg.fusion_tkns, cfg.fusion_heads)
-    xmm = xmm + _mlp(P, sd, f"{pre}.mlp", P.layer_norm(xmm, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], e))
+    xmm = xmm + _dp(drops, _factorized_attention(P, sd, f"{pre}.attn", xmm, xv, xa, cfg.fusion_tkns, cfg.fusion_heads))   # :283
+    xmm = xmm + _dp(drops, _mlp(P, sd, f"{pre}.mlp", P.layer_norm(xmm, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], e)))  # :288
     return xmm
 
 
@@ -347,7 +356,9 @@ def fusion_block(P: _Prec, sd, pre: str, xmm: Tensor, xv: Tensor, xa: Tensor, cf
 # --------------------------------------------------------------------------------------
 def encoder_forward(P: _Prec, sd, cfg: OracleConfig, image: Tensor, audio: Tensor,
                     image_ids_keep: Optional[Tensor] = None, audio_ids_keep: Optional[Tensor] = None,
-                    return_embs: bool = False):
+                    return_embs: bool = False, drops=None):
+    """``drops``: None, or an iterator over the DropPath scale vectors in the reference's call order -- per layer:
+    image block (attention, MLP), audio block (attention, MLP), fusion block (attention, MLP)."""
     B = image.shape[0]
     x_i = prepare_patch_tokens(P, sd, "encoder.image", image, image_ids_keep, cfg.patch)   # :92
     x_a = prepare_patch_tokens(P, sd, "encoder.audio", audio, audio_ids_keep, cfg.patch)   # :93
@@ -358,12 +369,12 @@ def encoder_forward(P: _Prec, sd, cfg: OracleConfig, image: Tensor, audio: Tenso
     for l in range(cfg.depth):                                                             # :99
         bi, ba = f"encoder.image.blocks.{l}", f"encoder.audio.blocks.{l}"
         if l not in fl:                                                                    # :100-102
-            x_i = vit_block(P, sd, bi, x_i, cfg.heads, cfg.enc_eps)
-            x_a = vit_block(P, sd, ba, x_a, cfg.heads, cfg.enc_eps)
+            x_i = vit_block(P, sd, bi, x_i, cfg.heads, cfg.enc_eps, drops)
+            x_a = vit_block(P, sd, ba, x_a, cfg.heads, cfg.enc_eps, drops)
         else:                                                                              # :104-107
-            _, n_i = vit_block(P, sd, bi, torch.cat((x_f, x_i), 1), cfg.heads, cfg.enc_eps).split((nF, nI), 1)
-            _, n_a = vit_block(P, sd, ba, torch.cat((x_f, x_a), 1), cfg.heads, cfg.enc_eps).split((nF, nA), 1)
-            x_f = fusion_block(P, sd, f"encoder.fusion_blocks.{l}", x_f, x_i, x_a, cfg)   # pre-block x_i / x_a
+            _, n_i = vit_block(P, sd, bi, torch.cat((x_f, x_i), 1), cfg.heads, cfg.enc_eps, drops).split((nF, nI), 1)
+            _, n_a = vit_block(P, sd, ba, torch.cat((x_f, x_a), 1), cfg.heads, cfg.enc_eps, drops).split((nF, nA), 1)
+            x_f = fusion_block(P, sd, f"encoder.fusion_blocks.{l}", x_f, x_i, x_a, cfg, drops)   # pre-block x_i / x_a
             x_i, x_a = n_i, n_a
         if return_embs:
             embs.append((x_i, x_a, x_f))
@@ -466,7 +477,7 @@ def classifier_state(cfg: OracleConfig, num_classes: int, seed: int = 0, input_n
 
 
 def classifier_forward(sd: Dict[str, Tensor], cfg: OracleConfig, image: Tensor, audio: Tensor, input_norm: bool = False,
-                       training: bool = True, freeze_encoder: bool = False, momentum: float = 0.1, eps: float = 1e-6):
+                       training: bool = True, freeze_encoder: bool = False, momentum: float = 0.1, eps: float = 1e-6, drops=None):
     """Returns (pred_image, pred_audio, pred_fusion) and the updated BatchNorm running statistics.  The reference
     runs this path in fp32 (configs/linprobe.yaml:35, finetune.yaml:50)."""
     P = _Prec(False)
@@ -474,7 +485,7 @@ def classifier_forward(sd: Dict[str, Tensor], cfg: OracleConfig, image: Tensor, 
         with torch.no_grad():
             xs = encoder_forward(P, sd, cfg, image, audio)
     else:
-        xs = encoder_forward(P, sd, cfg, image, audio)                                    # :47
+        xs = encoder_forward(P, sd, cfg, image, audio, drops=None if drops is None else iter(drops))   # :47
     preds, stats = [], {}
     for m, x in zip(("image", "audio", "fusion"), xs):
         f = x.mean(dim=1)                                                                 # :49
@@ -491,13 +502,13 @@ def classifier_forward(sd: Dict[str, Tensor], cfg: OracleConfig, image: Tensor, 
     return tuple(preds), stats
 
 
-def classifier_loss_and_grads(sd, cfg, image, audio, target_w, input_norm=False, training=True, freeze_encoder=False):
+def classifier_loss_and_grads(sd, cfg, image, audio, target_w, input_norm=False, training=True, freeze_encoder=False, drops=None):
     """Scalar = sum_m (pred_m * target_w).sum() -- a fixed linear functional of the three predictions, so that the
     gradient check does not depend on a loss the path does not own.  Returns (preds, stats, grads)."""
     trainable = lambda k: (k not in FROZEN_KEYS) and ("running_" not in k) and ("num_batches" not in k) and \
         not (freeze_encoder and k.startswith("encoder."))
     leaves = {k: (v.detach().clone().requires_grad_(True) if (v.is_floating_point() and trainable(k)) else v) for k, v in sd.items()}
-    preds, stats = classifier_forward(leaves, cfg, image, audio, input_norm, training, freeze_encoder)
+    preds, stats = classifier_forward(leaves, cfg, image, audio, input_norm, training, freeze_encoder, drops=drops)
     sum((p * target_w).sum() for p in preds).backward()
     grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}
     return tuple(p.detach() for p in preds), stats, grads

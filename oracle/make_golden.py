@@ -198,21 +198,42 @@ def classifier_fixture(out_dir):
     g = torch.Generator().manual_seed(5)
     tw = torch.randn(B, C, generator=g)
     saved = {}
-    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False)):
+    import timm.models.layers as shim_layers      # oracle/timm_shim: DropPath as the reference imports it
+    n_draws = 6 * cfg.depth                         # per layer: image block 2, audio block 2, fusion block 2 (reference call order)
+    gd = torch.Generator().manual_seed(9)
+    drops = [(torch.rand(B, generator=gd) < 0.8).float() / 0.8 for _ in range(n_draws)]
+    saved["droppath_scales"] = torch.stack(drops).numpy()
+    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False), ("finetune_droppath", False, False)):
+        dp = 0.2 if tag == "finetune_droppath" else 0.0
         torch.manual_seed(0)
         enc = DeepAVFusion(image_arch="vit_test", image_pretrained="", image_size=cfg.image_size,
                            audio_arch="vit_test", audio_pretrained="", audio_size=cfg.audio_size,
                            fusion_arch="factorized_mmi", fusion_layers=cfg.fusion_layers, num_fusion_tkns=cfg.fusion_tkns,
-                           fusion_mlp_ratio=cfg.fusion_mlp_ratio, fusion_attn_ratio=cfg.fusion_attn_ratio, fusion_num_heads=cfg.fusion_heads)
+                           fusion_mlp_ratio=cfg.fusion_mlp_ratio, fusion_attn_ratio=cfg.fusion_attn_ratio, fusion_num_heads=cfg.fusion_heads,
+                           drop_path=dp)
         model = AVClassifier(enc, C, freeze_encoder=freeze, input_norm=inorm)
         sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
         assert set(sd) == set(model.state_dict()), set(sd) ^ set(model.state_dict())
         model.load_state_dict(sd, strict=True)
         model.train()
-        preds = model(image, audio)
+        it = iter(drops)
+        orig_fwd = shim_layers.DropPath.forward
+
+        def injected(self, x):                      # the reference's DropPath modules, fed our masks in call order
+            if self.drop_prob == 0. or not self.training:
+                return x
+            return x * next(it).view(-1, *([1] * (x.ndim - 1)))
+        shim_layers.DropPath.forward = injected
+        try:
+            preds = model(image, audio)
+        finally:
+            shim_layers.DropPath.forward = orig_fwd
+        if dp:
+            assert next(it, None) is None, "the reference drew a different number of DropPath masks"
         sum((p * tw).sum() for p in preds).backward()
         ref_grads = {k: p.grad for k, p in model.named_parameters() if p.requires_grad and p.grad is not None}
-        opreds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
+        opreds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze,
+                                                           drops=drops if dp else None)
         for a, b in zip(opreds, preds):
             assert rel(a, b.detach()) < 1e-5, (tag, rel(a, b.detach()))
         assert set(grads) == set(ref_grads), (tag, set(grads) ^ set(ref_grads))

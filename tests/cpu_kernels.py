@@ -318,6 +318,18 @@ def head_bwd(dy, x, W, dW, db, need_dx):
     return dy @ W if need_dx else None
 
 
+def scale_rows_add(res, y, scale, rows_per_sample):
+    D = res.shape[-1]
+    s = scale.repeat_interleave(rows_per_sample)[:, None]
+    return (res.reshape(-1, D) + s * y.reshape(-1, D)).reshape(res.shape)
+
+
+def scale_rows(src, scale, rows_per_sample, want_f32=False, want_bf16=True):
+    D = src.shape[-1]
+    v = scale.repeat_interleave(rows_per_sample)[:, None] * src.reshape(-1, D)
+    return (v if want_f32 else None), (v.to(bf16) if want_bf16 else None)
+
+
 def launch_count():
     return 0
 

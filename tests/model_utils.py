@@ -17,7 +17,7 @@ def tiny_cfg(**kw) -> O.OracleConfig:
     return O.OracleConfig(**base)
 
 
-def build_model(cfg: O.OracleConfig, device="cpu"):
+def build_model(cfg: O.OracleConfig, device="cpu", drop_path=0.0):
     """Our drop-in AVMAE(DeepAVFusion) for an oracle config (ViT-B or a tiny test size)."""
     from deepavfusion_b200.models import AVMAE, DeepAVFusion, vits
 
@@ -29,18 +29,37 @@ def build_model(cfg: O.OracleConfig, device="cpu"):
     enc = DeepAVFusion(image_arch="vit_test", image_pretrained="", image_size=cfg.image_size,
                        audio_arch="vit_test", audio_pretrained="", audio_size=cfg.audio_size,
                        fusion_layers=cfg.fusion_layers, num_fusion_tkns=cfg.fusion_tkns,
-                       fusion_mlp_ratio=cfg.fusion_mlp_ratio, fusion_attn_ratio=cfg.fusion_attn_ratio, fusion_num_heads=cfg.fusion_heads)
+                       fusion_mlp_ratio=cfg.fusion_mlp_ratio, fusion_attn_ratio=cfg.fusion_attn_ratio, fusion_num_heads=cfg.fusion_heads,
+                       drop_path=drop_path)
     model = AVMAE(enc, enc.embed_dim, image_decoder_depth=cfg.dec_depth, image_mask_ratio=cfg.image_mask_ratio,
                   image_norm_loss=cfg.image_norm_loss, audio_decoder_depth=cfg.dec_depth, audio_mask_ratio=cfg.audio_mask_ratio,
                   audio_norm_loss=cfg.audio_norm_loss, decoder_dim=cfg.dec_dim, num_heads=cfg.dec_heads, mlp_ratio=cfg.dec_mlp_ratio)
     return model.to(device)
 
 
-def build_classifier(cfg: O.OracleConfig, num_classes: int, freeze_encoder: bool, input_norm: bool, device="cpu"):
+def build_classifier(cfg: O.OracleConfig, num_classes: int, freeze_encoder: bool, input_norm: bool, device="cpu", drop_path=0.0):
     """Our drop-in AVClassifier(DeepAVFusion) for an oracle config."""
     from deepavfusion_b200.models import AVClassifier
-    enc = build_model(cfg, "cpu").encoder
+    enc = build_model(cfg, "cpu", drop_path=drop_path).encoder
     return AVClassifier(enc, num_classes, freeze_encoder=freeze_encoder, input_norm=input_norm).to(device)
+
+
+@contextlib.contextmanager
+def inject_droppath(scales):
+    """Make the model's DropPath draws (functional.droppath_scale) return the given per-sample scale vectors in order."""
+    import deepavfusion_b200.functional as Fn
+    it, orig = iter(scales), Fn.droppath_scale
+
+    def fake(B, drop_prob, device):
+        s = next(it)
+        assert s.numel() == B
+        return s.to(device=device, dtype=torch.float32)
+    Fn.droppath_scale = fake
+    try:
+        yield it
+    finally:
+        Fn.droppath_scale = orig
+
 
 
 def make_inputs(cfg, B, seed=1):

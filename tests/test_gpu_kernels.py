@@ -393,3 +393,14 @@ def test_classifier_tail_kernels(K, B, n, D, C):
     edx = E.head_bwd(dout.cpu(), pooled.cpu(), W.cpu(), edW, edb, True)
     close(dx, edx, 1e-4, 1e-4, "head dx"); close(dW, edW, 1e-4, 1e-3, "head dW"); close(db, edb, 1e-4, 1e-3, "head db")
     assert K.head_bwd(dout, pooled, W, None, None, False) is None
+
+
+def test_droppath_row_kernels(K):
+    B, n, D = 6, 49, 768
+    res, y, dy = rnd(B * n, D, seed=50), rnd(B * n, D, seed=51), rnd(B * n, D, seed=52)
+    scale = torch.tensor([0.0, 1.25, 1.25, 0.0, 1.25, 1.25], device="cuda")
+    close(K.scale_rows_add(res, y, scale, n), E.scale_rows_add(res.cpu(), y.cpu(), scale.cpu(), n), 1e-6, 1e-6, "scale_rows_add")
+    f, b = K.scale_rows(dy, scale, n, want_f32=True, want_bf16=True)
+    ef, eb = E.scale_rows(dy.cpu(), scale.cpu(), n, want_f32=True, want_bf16=True)
+    close(f, ef, 1e-6, 1e-6, "scale_rows f32"); close(b, eb, 1e-2, 1e-2, "scale_rows bf16")
+    assert K.scale_rows(dy, scale, n)[0] is None

@@ -45,12 +45,13 @@ def test_tiny_fwd_bwd_vs_oracle(name, kw, B):
     assert glob <= 2e-2, glob
 
 
-@pytest.mark.parametrize("tag,freeze,inorm", [("linprobe", True, True), ("finetune", False, False), ("finetune_bn", False, True)])
-def test_classifier_vs_oracle(tag, freeze, inorm):
+@pytest.mark.parametrize("tag,freeze,inorm,dp", [("linprobe", True, True, 0.0), ("finetune", False, False, 0.0), ("finetune_bn", False, True, 0.0),
+                                                 ("finetune_droppath", False, False, 0.2)])
+def test_classifier_vs_oracle(tag, freeze, inorm, dp):
     """a11 / BASELINE configs 4-5 at test size: drop-in AVClassifier on cuda:0 (unmasked encoder + pool / BatchNorm /
     heads, forward and backward, then eval mode on the running statistics) against the oracle restatement."""
     from test_host_cpu import _classifier_case
-    _classifier_case("cuda", freeze, inorm)
+    _classifier_case("cuda", freeze, inorm, dp=dp)
 
 
 def test_classifier_golden_linprobe():

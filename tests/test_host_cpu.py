@@ -50,24 +50,30 @@ def test_model_orchestration_vs_oracle(emulated, kw, B):
     assert named["encoder.image.pos_embed"].grad is None
 
 
-@pytest.mark.parametrize("tag,freeze,inorm", [("linprobe", True, True), ("finetune", False, False), ("finetune_bn", False, True)])
-def test_classifier_orchestration_vs_oracle(emulated, tag, freeze, inorm):
-    """a11 (classifier.py:42-59): drop-in AVClassifier, emulated kernels, against the oracle restatement."""
-    _classifier_case("cpu", freeze, inorm)
+@pytest.mark.parametrize("tag,freeze,inorm,dp", [("linprobe", True, True, 0.0), ("finetune", False, False, 0.0), ("finetune_bn", False, True, 0.0),
+                                                 ("finetune_droppath", False, False, 0.2)])
+def test_classifier_orchestration_vs_oracle(emulated, tag, freeze, inorm, dp):
+    """a11 (classifier.py:42-59): drop-in AVClassifier, emulated kernels, against the oracle restatement; the
+    fine-tuning config's stochastic depth (configs/finetune.yaml:36) with the DropPath masks injected on both sides."""
+    _classifier_case("cpu", freeze, inorm, dp=dp)
 
 
-def _classifier_case(device, freeze, inorm, C=10, B=4):
+def _classifier_case(device, freeze, inorm, C=10, B=4, dp=0.0):
     cfg = U.tiny_cfg()
     sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
     image, audio = U.make_inputs(cfg, B)
     tw = torch.randn(B, C, generator=torch.Generator().manual_seed(5))
-    preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
-    model = U.build_classifier(cfg, C, freeze, inorm, device)
+    gd = torch.Generator().manual_seed(9)
+    drops = [(torch.rand(B, generator=gd) < 1 - dp).float() / (1 - dp) for _ in range(6 * cfg.depth)] if dp else None
+    preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze, drops=drops)
+    model = U.build_classifier(cfg, C, freeze, inorm, device, drop_path=dp)
     assert set(model.state_dict()) == set(sd)
     model.load_state_dict(sd, strict=True)
     assert model.train() is None                   # reference quirk: AVClassifier.train() returns None (classifier.py:61-64)
     assert model.encoder.training == (not freeze)
-    out = model(image.to(device), audio.to(device))
+    with U.inject_droppath(drops or []) as it:
+        out = model(image.to(device), audio.to(device))
+        assert next(it, None) is None                # same number of draws, same order as the reference (image, audio, fusion per layer)
     sum((p * tw.to(device)).sum() for p in out).backward()
     for p, r in zip(out, preds):
         rel = float((p.detach().cpu() - r).norm() / r.norm())
@@ -158,7 +164,7 @@ def test_encoder_api_contract(emulated):
 def test_unsupported_options_fail_loudly():
     from deepavfusion_b200.models import DeepAVFusion
     with pytest.raises(NotImplementedError):
-        DeepAVFusion(image_pretrained="", audio_pretrained="", drop_path=0.2)
+        DeepAVFusion(image_pretrained="", audio_pretrained="", attn_drop=0.1)
     with pytest.raises(NotImplementedError):
         DeepAVFusion(image_pretrained="", audio_pretrained="", fusion_arch="dense_mmi")
 

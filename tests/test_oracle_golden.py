@@ -100,9 +100,11 @@ def test_classifier_oracle_matches_reference_fixture():
     C, B = 10, 4
     image, audio = U.make_inputs(cfg, B)
     tw = torch.from_numpy(z["target_w"])
-    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False)):
+    drops = [torch.from_numpy(r) for r in z["droppath_scales"]]          # the masks the reference's DropPath modules were fed
+    for tag, freeze, inorm in (("linprobe", True, True), ("finetune", False, False), ("finetune_droppath", False, False)):
         sd = O.classifier_state(cfg, C, seed=0, input_norm=inorm)
-        preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze)
+        preds, stats, grads = O.classifier_loss_and_grads(sd, cfg, image, audio, tw, input_norm=inorm, training=True, freeze_encoder=freeze,
+                                                          drops=drops if tag.endswith("droppath") else None)
         for n, p in zip(("image", "audio", "fusion"), preds):
             ref = torch.from_numpy(z[f"{tag}_pred_{n}"])
             assert float((p - ref).norm() / ref.norm()) < 1e-5
