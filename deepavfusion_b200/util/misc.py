@@ -46,7 +46,8 @@ class Trainer:
         self.accum_iter = accum_iter
         self.accums = 0
         # bucket scheduler: gradient all-reduce (N > 1) and / or the optimizer step overlapped with backward
-        overlap_opt = isinstance(self.optimizer, FusedAdamW) and self.store.flat_g.is_cuda and os.environ.get("DAVF_OVERLAP_ADAMW", "1") != "0"
+        mode = os.environ.get("DAVF_OVERLAP_ADAMW", "1")         # "0": off; "force": also on CPU tensors (host-logic tests)
+        overlap_opt = isinstance(self.optimizer, FusedAdamW) and mode != "0" and (self.store.flat_g.is_cuda or mode == "force")
         self.sync = dist_utils.GradSync(self.store, bucket_mb=bucket_mb, optimizer=self.optimizer if overlap_opt else None) \
             if (self.distributed or overlap_opt) else None
         if self.distributed:

@@ -129,15 +129,44 @@ def test_lr_schedule_mirror():
     assert abs(lr - 1e-3 * 0.5) < 1e-9 and opt.param_groups[1]["lr"] == lr
 
 
+def test_bucketed_optimizer_step_equals_plain_step(monkeypatch):
+    """Trainer.step with the optimizer applied bucket by bucket from inside backward (GradSync.fuse_optimizer; forced on for
+    CPU tensors here) leaves exactly the parameters / moments / grad norm of backward followed by one whole-buffer step."""
+    cpu_kernels.install(monkeypatch)
+    from deepavfusion_b200.util.misc import Trainer
+    cfg = U.tiny_cfg()
+    image, audio = U.make_inputs(cfg, 2)
+    ni, na = U.make_noise(cfg, 2)
+    res = {}
+    for mode in ("force", "0"):
+        monkeypatch.setenv("DAVF_OVERLAP_ADAMW", mode)
+        model = U.build_model(cfg); model.load_state_dict(O.build_state(cfg, seed=0))
+        tr = Trainer(model, optimizer=torch.optim.AdamW(_groups(model), lr=1e-3, betas=(0.9, 0.95)), accum_iter=2, bucket_mb=0.25)
+        assert (tr.sync is not None and tr.sync.optimizer is not None) == (mode == "force")
+        for it in range(4):                              # two optimizer steps of two micro-steps each
+            with U.inject_rand([ni, na]):
+                li, la, _, _ = model(image, audio)
+            norm, _ = tr.step(li + la)
+            assert (norm is None) == (it % 2 == 0)
+            if it % 2 == 0:
+                assert float(tr.store.flat_g.abs().max()) > 0        # accumulated, not yet consumed
+        assert float(tr.store.flat_g.abs().max()) == 0.0 and tr.optimizer.n_steps == 2
+        res[mode] = (tr.store.flat_p.clone(), tr.optimizer.flat_m.clone(), tr.optimizer.flat_v.clone(), float(norm))
+    for a, b in zip(res["force"][:3], res["0"][:3]):
+        assert torch.equal(a, b)
+    assert abs(res["force"][3] - res["0"][3]) <= 1e-6 * res["0"][3]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _dp_worker(rank, world, port, out_dir):
+def _dp_worker(rank, world, port, out_dir, fused=False):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      DAVF_OVERLAP_ADAMW="force" if fused else "0")
     torch.set_num_threads(2)
     cpu_kernels.install()
     from deepavfusion_b200.util.misc import Trainer
@@ -153,13 +182,19 @@ def _dp_worker(rank, world, port, out_dir):
     for micro in range(2):
         with U.inject_rand([ni[sl], na[sl]]):
             li, la, _, _ = trainer.model(image[sl], audio[sl])
-        trainer.backward(li + la)
+        if fused:                                        # all-reduce + bucketed AdamW from inside backward (Trainer.step)
+            trainer.step(li + la)
+        else:
+            trainer.backward(li + la)
         if micro == 0:                                   # no_sync semantics: nothing reduced yet
             assert not any(trainer.sync.launched)
     grads = trainer.store.flat_g.clone() * float(trainer.optimizer.scal[2])
-    trainer.optimizer.step()
+    if fused:
+        assert float(grads.abs().max()) == 0.0 and trainer.optimizer.n_steps == 1
+    else:
+        trainer.optimizer.step()
     torch.save({"grads": grads, "names": trainer.store.names, "offsets": trainer.store.offsets,
-                "state": {k: v.clone() for k, v in model.state_dict().items()}}, os.path.join(out_dir, f"rank{rank}.pt"))
+                "state": {k: v.clone() for k, v in model.state_dict().items()}}, os.path.join(out_dir, f"rank{rank}{'f' if fused else ''}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -169,6 +204,11 @@ def test_data_parallel_gloo_world2(tmp_path, monkeypatch):
     mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert torch.equal(r0["grads"], r1["grads"])
+    # the same step with the all-reduce followed bucket by bucket by the fused AdamW (Trainer.step): identical parameters
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path), True), nprocs=world, join=True)
+    f0, f1 = torch.load(tmp_path / "rank0f.pt"), torch.load(tmp_path / "rank1f.pt")
+    for k in r0["state"]:
+        assert torch.equal(f0["state"][k], f1["state"][k]) and torch.equal(f0["state"][k], r0["state"][k]), f"fused step differs on {k}"
     for k in r0["state"]:
         assert torch.equal(r0["state"][k], r1["state"][k]), f"ranks diverged on {k}"
     # single process, full batch: the averaged 2-rank gradient equals the full-batch gradient
