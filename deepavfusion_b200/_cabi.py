@@ -89,6 +89,7 @@ SIGNATURES = {
     "davf_set_gemm_sms": (i, [i]),
     "davf_set_attn_impl": (i, [i]),
     "davf_launch_count": (i64, []),
+    "davf_launch_count_kind": (i64, [i]),
     "davf_mask_rank": (i, [vp, i, i, i, vp, vp, vp, vp]),
     "davf_patch_rows": (i, [vp, vp, vp, i, i, i, i, i, i, vp]),
     "davf_cast_rows_bf16": (i, [vp, vp, i64, i, i, i, i, vp]),

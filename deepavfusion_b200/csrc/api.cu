@@ -5,6 +5,7 @@
 namespace davf {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launch_kind[kNumKinds];
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -24,4 +25,8 @@ int davf_device_sm(void) {
   return major * 10 + minor;
 }
 int64_t davf_launch_count(void) { return davf::g_launches.load(); }
+int64_t davf_launch_count_kind(int kind) {
+  if (kind <= 0 || kind >= davf::kNumKinds) return davf::g_launches.load();
+  return davf::g_launch_kind[kind].load();
+}
 }

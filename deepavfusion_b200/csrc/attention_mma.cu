@@ -401,6 +401,7 @@ static int launch_fwd_nw(const davf_attn_fwd_args& a, cudaStream_t st) {
   }
   dim3 grid((a.Nq + QT - 1) / QT, a.B * a.H);
   kern<<<grid, NW * 32, smem, st>>>(a, Nkp);
+  g_launch_kind[kKindAttnMma].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -430,6 +431,7 @@ static int launch_bwd_nw(const davf_attn_bwd_args& a, cudaStream_t st) {
     configured = smem;
   }
   kern<<<a.B * a.H, NW * 32, smem, st>>>(a, Nqp, Nkp);
+  g_launch_kind[kKindAttnMma].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

@@ -12,6 +12,9 @@ namespace davf {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+// launches by kernel family (davf_launch_count_kind): 1 = CTA-pair tcgen05 GEMM, 2 = tcgen05 attention, 3 = mma.sync attention
+enum { kKindGemm2Cta = 1, kKindAttnTc = 2, kKindAttnMma = 3, kNumKinds = 4 };
+extern std::atomic<int64_t> g_launch_kind[kNumKinds];
 
 #define DAVF_CHECK_ARG(cond, ...)                      \
   do {                                                 \

@@ -908,6 +908,7 @@ static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
   cfg.numAttrs = CG > 1 ? 1 : 0;
   DAVF_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
   g_launches.fetch_add(1);
+  if (CG == 2) g_launch_kind[kKindGemm2Cta].fetch_add(1);
   return DAVF_OK;
 }
 

@@ -81,7 +81,11 @@ def _f32_rows(t: Tensor) -> Tensor:
 def _lowp_grad(st: ParamStore, dy2d: Tensor) -> Tensor:
     """bf16 copy of an incoming f32 gradient [rows, D]: the one its producer already wrote, else a cast launch."""
     lp = st.take_lowp_grad(dy2d)
-    return lp.view(dy2d.shape) if lp is not None else K.cast_rows_bf16(dy2d)
+    if lp is None:
+        return K.cast_rows_bf16(dy2d)
+    if lp.is_cuda:       # written on the producer's stream, read by this region's GEMMs on the current one
+        lp.record_stream(torch.cuda.current_stream())
+    return lp.view(dy2d.shape)
 
 
 def _new_lowp(like: Tensor) -> Tensor:

@@ -519,6 +519,14 @@ def launch_count() -> int:
     return int(_cabi.lib().davf_launch_count())
 
 
+KIND_GEMM_2CTA, KIND_ATTN_TC, KIND_ATTN_MMA = 1, 2, 3
+
+
+def launch_count_kind(kind: int) -> int:
+    """Launches of one kernel family so far (see davf_launch_count_kind)."""
+    return int(_cabi.lib().davf_launch_count_kind(int(kind)))
+
+
 def set_gemm_impl(impl: int) -> None:
     check(_cabi.lib().davf_set_gemm_impl(impl), "davf_set_gemm_impl")
 

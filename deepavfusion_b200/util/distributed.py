@@ -16,7 +16,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
-from ..params import ParamStore
+from ..params import ALIGN, ParamStore
 
 
 def is_dist_avail_and_initialized() -> bool:
@@ -77,7 +77,7 @@ class GradSync:
             b, e = store.span(k)
             cur.append(k)
             size += e - b
-            if size >= target:
+            if size >= target and b % ALIGN == 0:      # (a stacked k / v pair may start off the grid: never cut there)
                 self.buckets.append(cur)
                 cur, size = [], 0
         if cur:

@@ -50,3 +50,23 @@ def param_groups_pretrained(model, weight_decay=0.05, no_weight_decay_list=(), i
     for g in groups:
         g["params"] = [p for p in g["params"] if id(p) not in taken]
     return groups + pt
+
+
+def param_groups_lrd(model, weight_decay=0.05, no_weight_decay_list=(), layer_decay=0.75):
+    """lr_sched.py:25-58 (fine-tuning, eval_finetune.py:199-203): one (decay, no_decay) pair of groups per layer id
+    of ``model.params_layer_ids()``, each with ``lr_scale = layer_decay ** (top - layer)``; 1-D parameters and listed
+    names are not decayed.  Group order = order of first appearance in ``named_parameters()``."""
+    layer_of = {id(p): lid for p, lid in model.params_layer_ids()}
+    top = max(layer_of.values())
+    skip = set(no_weight_decay_list)
+    groups = {}
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        lid = layer_of[id(p)]
+        plain = p.ndim == 1 or name in skip
+        key = (lid, plain)
+        if key not in groups:
+            groups[key] = {"lr_scale": layer_decay ** (top - lid), "weight_decay": 0.0 if plain else weight_decay, "params": []}
+        groups[key]["params"].append(p)
+    return list(groups.values())

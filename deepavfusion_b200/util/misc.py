@@ -62,8 +62,18 @@ class Trainer:
         self.zero_grad()
 
     def broadcast_parameters(self):
-        """Rank 0 -> all, once (what the DDP constructor does, misc.py:34): one flat buffer."""
+        """Rank 0 -> all, once (what the DDP constructor does, misc.py:34): one flat buffer, then the module buffers.
+        The reference converts BatchNorm to SyncBatchNorm first (misc.py:33); the classifier's BatchNorm1d kernel
+        (AVClassifier(input_norm=True)) normalises with per-rank batch statistics, so a data-parallel run of it would
+        silently diverge from the reference: refuse it."""
+        for mod in self.model_without_ddp.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                raise NotImplementedError("data-parallel training with BatchNorm (AVClassifier(input_norm=True)) needs "
+                                          "SyncBatchNorm statistics (misc.py:33), which the classifier tail kernel does not "
+                                          "all-reduce; run lin-probe on one GPU or with input_norm=False")
         torch.distributed.broadcast(self.store.flat_p, src=0)
+        for b in self.model_without_ddp.buffers():
+            torch.distributed.broadcast(b, src=0)
         self.store.refresh_lowp(force=True)
 
     def module_dict(self):

@@ -37,13 +37,23 @@ class FusedAdamW(torch.optim.Optimizer):
                 k = store.index_of(p)
                 b, e = store.span(k)
                 if p.requires_grad:
-                    cg[b // ALIGN:e // ALIGN] = gi
+                    # the stacked pair-attention k / v tensors share a 64-element chunk when k ends off the ALIGN grid
+                    # (ParamStore.stacked): a chunk has ONE group, so both neighbours must agree on it
+                    c0, c1 = b // ALIGN, (b + p.numel() + ALIGN - 1) // ALIGN
+                    taken = cg[c0:c1]
+                    assert bool(((taken == 255) | (taken == gi)).all()), \
+                        f"{store.names[k]}: shares a {ALIGN}-element chunk with a parameter of another group"
+                    cg[c0:c1] = gi
                 self.state[p] = dict(step=torch.zeros((), dtype=torch.float32),
                                      exp_avg=self.flat_m[b:b + p.numel()].view(p.shape),
                                      exp_avg_sq=self.flat_v[b:b + p.numel()].view(p.shape))
         self.chunk_group = cg.to(dev)
         self.hp = torch.zeros(2 * ngroups, dtype=torch.float32, device=dev)
-        self._hp_host = torch.zeros(2 * ngroups, dtype=torch.float32, pin_memory=dev.type == "cuda")
+        # ring of pinned staging buffers: the host runs several (graph-replayed) steps ahead of the GPU, so the buffer of
+        # step t must not be rewritten before its queued H2D copy has executed; slot i is reused only after its event
+        self._hp_ring = [torch.zeros(2 * ngroups, dtype=torch.float32, pin_memory=dev.type == "cuda") for _ in range(8)]
+        self._hp_events = [None] * len(self._hp_ring)
+        self._hp_slot = 0
         self._hp_last = None
         # {beta1^t, beta2^t, grad_scale, -}: advanced on the device so a captured step replays correctly
         self.scal = torch.tensor([1.0, 1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
@@ -59,8 +69,17 @@ class FusedAdamW(torch.optim.Optimizer):
         for g in self.param_groups:
             vals += [float(g["lr"]), float(g["weight_decay"])]
         if vals != self._hp_last:
-            self._hp_host.copy_(torch.tensor(vals, dtype=torch.float32))
-            self.hp.copy_(self._hp_host, non_blocking=True)
+            k = self._hp_slot
+            self._hp_slot = (k + 1) % len(self._hp_ring)
+            if self._hp_events[k] is not None:
+                self._hp_events[k].synchronize()            # the copy that last read this slot (8 uploads ago) is done
+            host = self._hp_ring[k]
+            host.copy_(torch.tensor(vals, dtype=torch.float32))
+            self.hp.copy_(host, non_blocking=True)
+            if self.hp.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._hp_events[k] = ev
             self._hp_last = vals
 
     def set_grad_scale(self, scale: float) -> None:

@@ -48,6 +48,9 @@ int davf_set_gemm_2cta(int on);
 int davf_set_attn_impl(int impl);
 /* Number of kernel launches issued by this library since process start (bench gpu_launches). */
 int64_t davf_launch_count(void);
+/* The same, by kernel family: 1 = CTA-pair (cta_group::2) tcgen05 GEMM, 2 = tcgen05/TMEM attention, 3 = mma.sync attention
+ * (small-query cases); any other value = all.  Lets tests and benches prove which kernel variant served a call. */
+int64_t davf_launch_count_kind(int kind);
 
 /* ---- K2: MAE random masking ----------------------------------------------------------------
  * Replaces avmae.py:127-140 (rand -> argsort -> argsort -> slice -> gather) given the noise.

@@ -209,8 +209,10 @@ class _Prec:
     """amp=False: everything fp32.  amp=True: CUDA bf16-autocast semantics -- ``linear`` /
     ``matmul`` cast operands to bf16 and return bf16; ``layer_norm`` / ``softmax`` return fp32."""
 
-    def __init__(self, amp: bool):
+    def __init__(self, amp: bool, sdpa: bool = False):
         self.amp = amp
+        self.sdpa = sdpa      # ViT-block attention through F.scaled_dot_product_attention (timm 0.9.2 ``fused_attn``):
+                              # only bench.py's eager-bf16-on-GPU leg sets it; every parity use keeps the explicit form
 
     def linear(self, x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
         if self.amp:
@@ -242,7 +244,7 @@ def random_masking(noise: Tensor, mask_ratio: float):
     ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
     len_keep = int(L * (1 - mask_ratio))                      # :132
     ids_keep = ids_shuffle[:, :len_keep]
-    mask = torch.ones(N, L, dtype=torch.float32)
+    mask = torch.ones(N, L, dtype=torch.float32, device=noise.device)
     mask[:, :len_keep] = 0
     mask = torch.gather(mask, 1, ids_restore)                 # :140
     return ids_keep, mask, ids_restore
@@ -274,6 +276,9 @@ def _attention(P: _Prec, sd, pre: str, x: Tensor, heads: int) -> Tensor:
     qkv = P.linear(x, sd[f"{pre}.qkv.weight"], sd[f"{pre}.qkv.bias"])
     qkv = qkv.reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
+    if P.sdpa:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+        return P.linear(o, sd[f"{pre}.proj.weight"], sd[f"{pre}.proj.bias"])
     s = P.matmul(q, k.transpose(-2, -1)).float() * hd ** -0.5
     a = P.softmax(s)
     o = P.matmul(a.to(v.dtype) if P.amp else a, v)
@@ -431,10 +436,10 @@ def forward_loss(target: Tensor, pred: Tensor, mask: Tensor, norm_pix_loss: bool
 # a8: AVMAE.forward  (avmae.py:216-236)
 # --------------------------------------------------------------------------------------
 def avmae_forward(sd: Dict[str, Tensor], cfg: OracleConfig, image: Tensor, audio: Tensor,
-                  noise_image: Tensor, noise_audio: Tensor, amp: bool = False) -> Dict[str, Tensor]:
+                  noise_image: Tensor, noise_audio: Tensor, amp: bool = False, sdpa: bool = False) -> Dict[str, Tensor]:
     """Returns a dict with the reference's 4 outputs plus the intermediate tensors parity tests
     compare (ids, masks, encoder outputs)."""
-    P = _Prec(amp)
+    P = _Prec(amp, sdpa)
     ik, im, ir = random_masking(noise_image, cfg.image_mask_ratio)                        # :220
     ak, am, ar = random_masking(noise_audio, cfg.audio_mask_ratio)                        # :221
     x_i, x_a, x_f = encoder_forward(P, sd, cfg, image, audio, ik, ak)                     # :224

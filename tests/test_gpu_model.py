@@ -84,15 +84,31 @@ def test_vitb_golden_fwd_bwd():
     assert close(pi[:, :4, :16], gold["pred_image_head"]) < 3e-2
     assert close(pa[:, :4, :16], gold["pred_audio_head"]) < 3e-2
     named = dict(model.named_parameters())
-    norms = {k: named[k].grad.float().norm().item() for k in meta["grad_keys"]}
+    keys = meta["grad_keys"]
+    gn_ref = float(gold["grad_norm_global"])
+    # (1) against the fixture of the REAL reference: per-tensor norms AND the leading elements of every gradient tensor
+    # (a transposed / mis-routed gradient of the right norm fails the element check)
+    norms = {k: named[k].grad.float().norm().item() for k in keys}
     gn = sum(v ** 2 for v in norms.values()) ** 0.5
-    assert abs(gn - float(gold["grad_norm_global"])) <= 1e-2 * float(gold["grad_norm_global"]), (gn, float(gold["grad_norm_global"]))
+    assert abs(gn - gn_ref) <= 1e-2 * gn_ref, (gn, gn_ref)
     bad = []
-    for i, k in enumerate(meta["grad_keys"]):
+    for i, k in enumerate(keys):
         ref = float(gold["grad_norms"][i])
-        if ref > 1e-4 * float(gold["grad_norm_global"]) and abs(norms[k] - ref) > 5e-2 * ref:
+        if ref > 1e-4 * gn_ref and abs(norms[k] - ref) > 5e-2 * ref:
             bad.append((k, norms[k], ref))
+        g = named[k].grad.detach().float().cpu().flatten()[:8]
+        h = torch.from_numpy(gold["grad_heads"][i][:g.numel()])
+        n_el = max(named[k].numel(), 1)
+        tol = 0.1 * float(h.abs().max()) + 4.0 * ref / n_el ** 0.5 * 0.03 + 1e-5 * gn_ref     # bf16 error ~3 % of the tensor's rms
+        if float((g - h).abs().max()) > tol:
+            bad.append((k, "head", g.tolist(), h.tolist()))
     assert not bad, bad[:5]
+    # (2) every gradient tensor element-wise against the oracle (itself pinned to the reference by make_golden.py)
+    _, grads = O.loss_and_grads(sd, cfg, image, audio, ni, na)
+    _, amp_grads = O.loss_and_grads(sd, cfg, image, audio, ni, na, amp=True)
+    failures, worst, glob = U.grad_report(named, grads, amp_grads)
+    assert not failures, f"{len(failures)} gradient tensors out of tolerance, e.g. {failures[:5]}"
+    assert glob <= 2e-2, glob
     # encoder-only unmasked forward (AVMAE.forward_encoder; BASELINE config 4 path)
     with torch.no_grad():
         xi, xa, xf = model.forward_encoder(image.cuda(), audio.cuda())
@@ -219,3 +235,62 @@ def test_graph_step_async_host_inputs_match_device_inputs():
     for a, b in zip(seqs["device"], seqs["async"]):
         for x, y in zip(a, b):
             assert abs(x - y) <= 2e-3 * abs(x) + 1e-6, (seqs["device"], seqs["async"])
+
+
+def test_graph_capture_is_side_effect_free_and_accumulates_like_eager():
+    """GraphedTrainStep (a) leaves parameters, Adam moments, beta^t and the step counters exactly as it found them (its
+    warm-up steps and capture pass must not train) and (b) with accum_iter = 2 -- two graphs: accumulate-only micro-step
+    and final micro-step with the fused AdamW, misc.py:144-148 -- walks the same trajectory as the eager Trainer."""
+    from deepavfusion_b200.util.misc import Trainer
+    from deepavfusion_b200.util.graphed import GraphedTrainStep
+    cfg = U.tiny_cfg()
+    sd = O.build_state(cfg, seed=0)
+    B, accum, steps = 3, 2, 2
+    micro = [tuple(t.cuda() for t in U.make_inputs(cfg, B, seed=20 + i)) for i in range(accum)]
+    ni, na = (t.cuda() for t in U.make_noise(cfg, B))
+    static = {tuple(ni.shape): ni, tuple(na.shape): na}
+    orig_rand = torch.rand
+
+    def fake_rand(*size, **kw):                      # the same mask noise in every step, eager and captured (device-side clone)
+        return static[tuple(size)].clone()
+    torch.rand = fake_rand
+    try:
+        runs = {}
+        for mode in ("eager", "graph"):
+            model = U.build_model(cfg, "cuda")
+            model.load_state_dict(sd, strict=True)
+            tr = Trainer(model, optimizer=torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05), accum_iter=accum)
+            norms = []
+            if mode == "graph":
+                opt = tr.optimizer
+                before = [t.clone() for t in (tr.store.flat_p, tr.store.flat_lp, tr.store.flat_g, opt.flat_m, opt.flat_v, opt.scal)]
+                g = GraphedTrainStep(tr, *micro[0], warmup=2)
+                after = (tr.store.flat_p, tr.store.flat_lp, tr.store.flat_g, opt.flat_m, opt.flat_v, opt.scal)
+                for b, a in zip(before, after):
+                    assert torch.equal(b, a), "graph construction changed training state"
+                assert opt.n_steps == 0 and int(tr.n_steps) == 0 and tr.accums == 0
+                assert g.graph_micro is not None and g.launches_micro > 0 and g.launches_final > g.launches_micro
+            for _ in range(steps):
+                for m in range(accum):
+                    if mode == "graph":
+                        out = g(*micro[m])
+                        norm = out[-1]
+                        assert (norm is None) == (m < accum - 1)
+                    else:
+                        li, la, _, _ = model(*micro[m])
+                        norm, _ = tr.step(li + la)
+                    if norm is not None:
+                        norms.append(float(norm))
+            torch.cuda.synchronize()
+            assert tr.optimizer.n_steps == steps and int(tr.n_steps) == steps
+            runs[mode] = (tr.store.flat_p.clone(), tr.optimizer.flat_m.clone(), tr.optimizer.flat_v.clone(), norms)
+            if mode == "graph":
+                del g
+    finally:
+        torch.rand = orig_rand
+    (pe, me, ve, ne), (pg, mg, vg, ng) = runs["eager"], runs["graph"]
+    assert len(ne) == len(ng) == steps
+    for a, b in zip(ne, ng):
+        assert abs(a - b) <= 2e-3 * abs(a), (ne, ng)
+    assert float((pe - pg).norm()) <= 1e-5 * float(pe.norm())
+    assert float((me - mg).norm()) <= 2e-3 * float(me.norm()) and float((ve - vg).norm()) <= 2e-3 * float(ve.norm())

@@ -193,3 +193,44 @@ def test_cabi_exports_every_declared_symbol():
     # argument validation happens before any CUDA call
     assert lib.davf_set_gemm_impl(7) == -1 and b"set_gemm_impl" in lib.davf_last_error()
     assert lib.davf_mask_rank(None, 1, 4, 9, None, None, None, None) == -1
+
+
+def test_flop_model_matches_survey_constants():
+    """bench.py's FLOPs per clip-pair (util/flops.py) reproduce the four constants SURVEY.md 8(d) derives for the BASELINE
+    configurations, and the pair-factorisation discount the survey says to subtract."""
+    from deepavfusion_b200.util import flops as F
+    vgg, aset = F.vggsound_pretrain(), F.audioset_pretrain()
+    cls = F.unmasked_classifier(310)
+    assert abs(F.gflop_forward(vgg, factorised=False) - 39.01) < 0.01 and abs(F.gflop_step(vgg, factorised=False) - 116.77) < 0.01
+    assert abs(F.gflop_forward(aset, factorised=False) - 43.27) < 0.01 and abs(F.gflop_step(aset, factorised=False) - 129.55) < 0.01
+    assert abs(F.gflop_forward(cls, factorised=False) - 66.07) < 0.01 and abs(F.gflop_step(cls, factorised=False) - 197.94) < 0.01
+    assert abs((F.gflop_step(vgg, False) - F.gflop_step(vgg, True)) - 5.94) < 0.01
+    assert abs((F.gflop_step(aset, False) - F.gflop_step(aset, True)) - 9.51) < 0.01
+    b = F.forward_breakdown(vgg, factorised=False)
+    for k, v in dict(patch_embed=0.27, image_blocks=9.38, audio_blocks=4.17, fusion_blocks=5.88, decoder_embed=0.10,
+                     image_decoder=12.33, audio_decoder=6.71, pred=0.18).items():
+        assert abs(b[k] / 1e9 - v) < 0.006, (k, b[k] / 1e9, v)
+
+
+def test_param_groups_lrd_mirror():
+    """lr_sched.py:25-58: one (decay, no-decay) group pair per layer id with lr_scale = decay ** (top - layer)."""
+    from deepavfusion_b200.util import lr_sched
+    cfg = U.tiny_cfg()
+    model = U.build_classifier(cfg, 10, False, False, "cpu")
+    no_wd = [n for n, p in model.named_parameters() if "bias" in n or "norm" in n]
+    groups = lr_sched.param_groups_lrd(model, 0.05, no_weight_decay_list=no_wd, layer_decay=0.75)
+    layer_of = {id(p): l for p, l in model.params_layer_ids()}
+    top = max(layer_of.values())
+    seen = set()
+    for g in groups:
+        lids = {layer_of[id(p)] for p in g["params"]}
+        assert len(lids) == 1
+        lid = lids.pop()
+        assert abs(g["lr_scale"] - 0.75 ** (top - lid)) < 1e-12
+        for p in g["params"]:
+            assert id(p) not in seen
+            seen.add(id(p))
+            assert (g["weight_decay"] == 0.0) == (p.ndim == 1 or any(p is q for n, q in model.named_parameters() if n in no_wd))
+    assert seen == {id(p) for p in model.parameters() if p.requires_grad}
+    heads = [g for g in groups if any(p is model.image_head.weight for p in g["params"])]
+    assert heads and heads[0]["lr_scale"] == 1.0
