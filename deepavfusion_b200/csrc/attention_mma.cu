@@ -445,6 +445,11 @@ static int launch_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
 
 int attn_simt_fwd(const davf_attn_fwd_args* a, cudaStream_t st);
 int attn_simt_bwd(const davf_attn_bwd_args* a, cudaStream_t st);
+// tcgen05 / TMEM / TMA kernels (attention_tc.cu): every problem with more than 16 query rows and head dim 64 / 32
+bool attn_tc_fwd_ok(const davf_attn_fwd_args& a);
+bool attn_tc_bwd_ok(const davf_attn_bwd_args& a);
+int attn_tc_fwd(const davf_attn_fwd_args& a, cudaStream_t st);
+int attn_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st);
 static std::atomic<int> g_attn_impl{0};
 
 static bool s8(int64_t x) { return x % 8 == 0; }
@@ -454,7 +459,7 @@ static bool s8(int64_t x) { return x % 8 == 0; }
 using namespace davf;
 
 extern "C" int davf_set_attn_impl(int impl) {
-  DAVF_CHECK_ARG(impl == 0 || impl == 1, "set_attn_impl: %d", impl);
+  DAVF_CHECK_ARG(impl >= 0 && impl <= 2, "set_attn_impl: %d", impl);
   g_attn_impl.store(impl);
   return DAVF_OK;
 }
@@ -468,6 +473,7 @@ extern "C" int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s) 
   if (a->B == 0) return DAVF_OK;
   cudaStream_t st = as_stream(s);
   if (g_attn_impl.load() == 1) return attn_simt_fwd(a, st);
+  if (g_attn_impl.load() == 0 && attn_tc_fwd_ok(*a)) return attn_tc_fwd(*a, st);
   if (a->dqk == 64 && a->dv == 64) return launch_fwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_fwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_fwd<16, 64>(*a, st);
@@ -486,6 +492,7 @@ extern "C" int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s) 
   if (a->B == 0) return DAVF_OK;
   cudaStream_t st = as_stream(s);
   if (g_attn_impl.load() == 1) return attn_simt_bwd(a, st);
+  if (g_attn_impl.load() == 0 && attn_tc_bwd_ok(*a)) return attn_tc_bwd(*a, st);
   if (a->dqk == 64 && a->dv == 64) return launch_bwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_bwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_bwd<16, 64>(*a, st);

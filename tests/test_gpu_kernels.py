@@ -266,12 +266,24 @@ def test_gemm_all_modes(impl, streamk):
 # ---------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,Nq,Nk,dqk,dv,skip", [(4, 12, 49, 81, 64, 64, 32), (3, 16, 228, 228, 32, 32, 0), (5, 12, 16, 8, 16, 64, 0),
                                                    (2, 12, 8, 19, 64, 64, 0), (2, 2, 4, 1, 64, 64, 0), (2, 12, 196, 228, 64, 64, 32),
-                                                   (2, 16, 128, 128, 32, 32, 0), (1, 2, 65, 129, 64, 64, 0)])
-@pytest.mark.parametrize("impl", [0, 1], ids=["mma", "simt"])
+                                                   (2, 16, 128, 128, 32, 32, 0), (1, 2, 65, 129, 64, 64, 0),
+                                                   # more work items than SMs: the persistent loops, stage ring and barrier phases
+                                                   (20, 16, 228, 228, 32, 32, 0), (40, 12, 49, 81, 64, 64, 32), (26, 12, 19, 51, 64, 64, 32),
+                                                   (30, 12, 96, 128, 64, 64, 32), (21, 16, 128, 128, 32, 32, 0), (7, 12, 196, 228, 64, 64, 32),
+                                                   (3, 3, 17, 17, 32, 32, 0), (2, 4, 256, 256, 64, 64, 0), (5, 2, 130, 20, 32, 32, 0)])
+@pytest.mark.parametrize("impl", [0, 2, 1], ids=["tcgen05", "mma", "simt"])
 def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
+    """impl 0 = product dispatch: tcgen05 / TMEM / TMA kernels for > 16 query rows at head dim 64 / 32 (asserted through the
+    per-family launch counter), mma.sync kernels for the tiny fusion-token problems; 2 = mma.sync everywhere; 1 = CUDA-core checker."""
+    if impl == 1 and B * H * Nq * Nk > 3_000_000:
+        pytest.skip("checker kernel: small cases only")
     K.set_attn_impl(impl)
     try:
+        n0 = K.launch_count_kind(K.KIND_ATTN_TC)
         _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
+        tc = K.launch_count_kind(K.KIND_ATTN_TC) - n0
+        eligible = impl == 0 and Nq > 16 and dqk == dv and dqk in (32, 64)
+        assert tc == (2 if eligible else 0), tc          # forward + the one-pass backward (the two-pass backward has no forward output)
     finally:
         K.set_attn_impl(0)
 

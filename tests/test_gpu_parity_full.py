@@ -22,7 +22,7 @@ from oracle import avmae_oracle as O
 import model_utils as U
 
 pytestmark = pytest.mark.gpu
-REQUIRE_ATTN_TC = False     # flipped on when the tcgen05 attention serves these shapes
+REQUIRE_ATTN_TC = True
 
 
 def _kinds():
