@@ -115,21 +115,25 @@ struct AttnTcFwdParams {
   float scale;
 };
 
+// Work item = (batch, head, 128-query tile).  Every phase of an item hangs on the previous one (load -> S -> softmax ->
+// P V -> store), so ONE item per SM leaves the tensor pipe, the MUFU and the TMA unit idle in turn.  The kernel is
+// therefore sized for TWO resident CTAs per SM that interleave their phases:
+//   TMEM   NKP columns per CTA: S = Q K^T in [0, NKP); O = P V overwrites columns [0, 64) once the softmax has consumed S
+//   smem   Q | K | X | V.  P (bf16, NKP / 64 tiles of [128 q][64 keys]) is written over Q and K, which are dead once S
+//          has been computed (NKP = 256: P also covers X); X is the output staging tile.  96 KB (NKP = 256) / 64 KB (128).
 // D = head dim (64 or 32), NKP = key capacity of the shared-memory tiles (128 or 256)
 template <int D, int NKP>
-__global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_constant__ AttnTcFwdParams p) {
+__global__ void __launch_bounds__(192, 2) attn_tc_fwd_kernel(const __grid_constant__ AttnTcFwdParams p) {
   constexpr uint32_t KV_BYTES = NKP * 128;
-  constexpr uint32_t STAGE_BYTES = kTile + 2 * KV_BYTES;          // Q tile | K | V
-  constexpr uint32_t P_BYTES = (NKP / 64) * kTile;
-  constexpr uint32_t TMEM_COLS = NKP == 256 ? 512 : 256;
-  constexpr uint32_t O_COL = NKP;                                   // S: columns [0, NKP), O: [NKP, NKP + 64)
+  constexpr uint32_t LOAD_BYTES = kTile + 2 * KV_BYTES;
+  constexpr uint32_t TMEM_COLS = NKP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t p_base = smem_base + 2 * STAGE_BYTES;
-  const uint32_t bar_base = p_base + P_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
-  const uint32_t s_ready = bar_base + 32u, p_ready = bar_base + 40u, o_ready = bar_base + 48u, tmem_ptr_addr = bar_base + 56u;
+  const uint32_t qs = smem_base, ks = qs + kTile, xs = ks + KV_BYTES, vs = xs + kTile;
+  const uint32_t p_base = smem_base;                                // P tiles alias Q | K (| X)
+  const uint32_t bar_base = vs + KV_BYTES;
+  const uint32_t full_bar = bar_base, s_ready = bar_base + 8u, p_ready = bar_base + 16u, o_ready = bar_base + 24u,
+                 o_cons = bar_base + 32u, stg_free = bar_base + 40u, tmem_ptr_addr = bar_base + 48u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -137,10 +141,12 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tk)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tv)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.to)) : "memory");
-    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(full_bar, 1);
     mbar_init(s_ready, 1);
     mbar_init(p_ready, 4);
     mbar_init(o_ready, 1);
+    mbar_init(o_cons, 4);
+    mbar_init(stg_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -161,20 +167,33 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
   auto koff_of = [&](int h) { return D == 64 ? 0u : (uint32_t)(h & 1) * 64u; };   // byte offset of head h inside it
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: loads of the next item, store of the finished one =====================
     const bool leader = elect_one();
+    auto load = [&](int w) {
+      int b, h, qt;
+      decode(w, b, h, qt);
+      if (leader) {
+        mbar_expect_tx(full_bar, LOAD_BYTES);
+        tma_load_3d(qs, &p.tq, full_bar, col_of(h), qt * 128, b);
+        tma_load_3d(ks, &p.tk, full_bar, col_of(h), 0, b);
+        tma_load_3d(vs, &p.tv, full_bar, col_of(h), 0, b);
+      }
+    };
+    if ((int)blockIdx.x < items) load(blockIdx.x);
+    __syncwarp();
     int it = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       int b, h, qt;
       decode(w, b, h, qt);
-      const int s = it & 1;
-      mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1u);
+      mbar_wait(o_ready, it & 1);                                  // every MMA of this item has retired: Q / K / V (and P) are dead
+      if (w + (int)gridDim.x < items) load(w + gridDim.x);
+      __syncwarp();
+      mbar_wait(o_cons, it & 1);                                   // the staging tile is written
       if (leader) {
-        const uint32_t qs = smem_base + s * STAGE_BYTES, ks = qs + kTile, vs = ks + KV_BYTES;
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        tma_load_3d(qs, &p.tq, full_bar(s), col_of(h), qt * 128, b);
-        tma_load_3d(ks, &p.tk, full_bar(s), col_of(h), 0, b);
-        tma_load_3d(vs, &p.tv, full_bar(s), col_of(h), 0, b);
+        tma_store_3d(&p.to, xs, h * D, qt * 128, b);               // rows >= Nq are clipped by the TMA unit
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(stg_free);
       }
       __syncwarp();
     }
@@ -187,12 +206,10 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       int b, h, qt;
       decode(w, b, h, qt);
-      const int s = it & 1;
-      const uint32_t qs = smem_base + s * STAGE_BYTES, ks = qs + kTile, vs = ks + KV_BYTES;
       const uint32_t koff = koff_of(h);
-      mbar_wait(full_bar(s), (it >> 1) & 1);
+      mbar_wait(full_bar, it & 1);
+      if (it > 0) mbar_wait(o_cons, (it - 1) & 1);               // O of the previous item has been read out of columns [0, 64)
       tc_fence_after();
-      // the S columns are free: the softmax warps signalled p_ready of the previous item after their last read
       if (leader) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
       tc_fence_after();
       if (leader) {
         for (int kk = 0; kk < nk16 / 16; ++kk)
-          umma_f16(tmem_base + O_COL, make_smem_desc(p_base + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
+          umma_f16(tmem_base, make_smem_desc(p_base + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
                    make_smem_desc(vs + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
         umma_commit(o_ready);
       }
@@ -221,45 +238,71 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       int b, h, qt;
       decode(w, b, h, qt);
-      const int s = it & 1;
       const bool live = qt * 128 + quad * 32 < p.Nq;               // warp-uniform: this warp owns at least one real query
       mbar_wait(s_ready, it & 1);
       tc_fence_after();
       float mx = -INFINITY, l = 0.f;
+      const int nch = (nk16 + 31) >> 5;                            // 32-column chunks of the score row
+      uint32_t va[32], vb[32];
       if (live) {
-        for (int c = 0; c < nk16; c += 32) {                       // pass 1: row max
-          uint32_t v[32];
-          tmem_ld_32x32b_x32_issue(trow + c, v);
-          tmem_ld_wait(v);
-          if (c + 32 <= p.Nk) {
+        // pass 1: row max.  The TMEM load of chunk c + 1 is in flight while chunk c is reduced.
+        auto reduce_max = [&](const uint32_t (&v)[32], int c) {
+          if (c * 32 + 32 <= p.Nk) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = (c + e < p.Nk) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+            for (int e = 0; e < 32; ++e) mx = (c * 32 + e < p.Nk) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+          }
+        };
+        tmem_ld_32x32b_x32_issue(trow, va);
+        tmem_ld_wait(va);
+        for (int c = 0; c < nch; c += 2) {
+          if (c + 1 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 1) * 32, vb);
+          reduce_max(va, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait(vb);
+            if (c + 2 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 2) * 32, va);
+            reduce_max(vb, c + 1);
+            if (c + 2 < nch) tmem_ld_wait(va);
           }
         }
-        const float m2 = mx * sl;
-        for (int c = 0; c < nk16; c += 32) {                       // pass 2: p = 2^(s sl - m2), row sum, bf16 P tile
-          uint32_t v[32];
-          tmem_ld_32x32b_x32_issue(trow + c, v);
-          tmem_ld_wait(v);
+      }
+      const float m2 = mx * sl;
+      if (it > 0) mbar_wait(stg_free, (it - 1) & 1);               // the TMA store of the previous item has read X (P's last tile when NKP = 256)
+      if (live) {
+        // pass 2: p = 2^(s sl - m2), row sum, bf16 P tile (Q and K are dead: S is complete)
+        auto emit = [&](const uint32_t (&v)[32], int c) {
           float pr[32];
-          if (c + 32 <= p.Nk) {
+          if (c * 32 + 32 <= p.Nk) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) pr[e] = ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2));
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) pr[e] = (c + e < p.Nk) ? ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2)) : 0.f;
+            for (int e = 0; e < 32; ++e) pr[e] = (c * 32 + e < p.Nk) ? ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2)) : 0.f;
           }
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) l += pr[e];
-          const uint32_t chunk = p_base + (uint32_t)(c >> 6) * kTile + (uint32_t)row * 128u;
-          const uint32_t j0 = (uint32_t)((c & 63) >> 3);
+          for (int e = 0; e < 32; e += 4) { s0 += pr[e]; s1 += pr[e + 1]; s2 += pr[e + 2]; s3 += pr[e + 3]; }
+          l += (s0 + s1) + (s2 + s3);
+          const uint32_t chunk = p_base + (uint32_t)(c >> 1) * kTile + (uint32_t)row * 128u;
+          const uint32_t j0 = (uint32_t)(c & 1) * 4u;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts_128(chunk + (((j0 + j) ^ sw) << 4), pack_bf16x2(pr[8 * j], pr[8 * j + 1]), pack_bf16x2(pr[8 * j + 2], pr[8 * j + 3]),
                     pack_bf16x2(pr[8 * j + 4], pr[8 * j + 5]), pack_bf16x2(pr[8 * j + 6], pr[8 * j + 7]));
+        };
+        tmem_ld_32x32b_x32_issue(trow, va);
+        tmem_ld_wait(va);
+        for (int c = 0; c < nch; c += 2) {
+          if (c + 1 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 1) * 32, vb);
+          emit(va, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait(vb);
+            if (c + 2 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 2) * 32, va);
+            emit(vb, c + 1);
+            if (c + 2 < nch) tmem_ld_wait(va);
+          }
         }
       }
       fence_async_smem();                                          // generic-proxy P writes -> visible to tcgen05.mma
@@ -267,49 +310,40 @@ __global__ void __launch_bounds__(192, 1) attn_tc_fwd_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
       const int q = qt * 128 + row;
-      if (live && q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (mx * sl + log2f(l)) * kLn2Tc;
+      if (live && q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m2 + log2f(l)) * kLn2Tc;
       const float inv_l = live ? 1.0f / l : 0.f;
 
       mbar_wait(o_ready, it & 1);
       tc_fence_after();
-      // every MMA of this item has retired: the stage's Q tile is dead and becomes the output staging tile
-      const uint32_t stg = smem_base + s * STAGE_BYTES;
       if (live) {
         if (D == 64) {
-          uint32_t o0[32], o1[32];
-          tmem_ld_32x32b_x32_issue(trow + O_COL, o0);
-          tmem_ld_32x32b_x32_issue(trow + O_COL + 32, o1);
-          tmem_ld_wait(o0);
-          tmem_ld_wait(o1);
+          tmem_ld_32x32b_x32_issue(trow, va);
+          tmem_ld_32x32b_x32_issue(trow + 32, vb);
+          tmem_ld_wait(va);
+          tmem_ld_wait(vb);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t* z = j < 4 ? o0 + 8 * j : o1 + 8 * (j - 4);
-            sts_128(stg + (uint32_t)row * 128u + (((uint32_t)j ^ sw) << 4),
+            const uint32_t* z = j < 4 ? va + 8 * j : vb + 8 * (j - 4);
+            sts_128(xs + (uint32_t)row * 128u + (((uint32_t)j ^ sw) << 4),
                     pack_bf16x2(__uint_as_float(z[0]) * inv_l, __uint_as_float(z[1]) * inv_l), pack_bf16x2(__uint_as_float(z[2]) * inv_l, __uint_as_float(z[3]) * inv_l),
                     pack_bf16x2(__uint_as_float(z[4]) * inv_l, __uint_as_float(z[5]) * inv_l), pack_bf16x2(__uint_as_float(z[6]) * inv_l, __uint_as_float(z[7]) * inv_l));
           }
         } else {
-          uint32_t o0[32];
-          tmem_ld_32x32b_x32_issue(trow + O_COL + (uint32_t)(h & 1) * 32u, o0);     // this head's half of the N = 64 accumulator
-          tmem_ld_wait(o0);
+          tmem_ld_32x32b_x32_issue(trow + (uint32_t)(h & 1) * 32u, va);        // this head's half of the N = 64 accumulator
+          tmem_ld_wait(va);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t* z = o0 + 8 * j;
-            sts_128(stg + (uint32_t)row * 64u + ((uint32_t)j << 4),
+            const uint32_t* z = va + 8 * j;
+            sts_128(xs + (uint32_t)row * 64u + ((uint32_t)j << 4),
                     pack_bf16x2(__uint_as_float(z[0]) * inv_l, __uint_as_float(z[1]) * inv_l), pack_bf16x2(__uint_as_float(z[2]) * inv_l, __uint_as_float(z[3]) * inv_l),
                     pack_bf16x2(__uint_as_float(z[4]) * inv_l, __uint_as_float(z[5]) * inv_l), pack_bf16x2(__uint_as_float(z[6]) * inv_l, __uint_as_float(z[7]) * inv_l));
           }
         }
       }
-      fence_async_smem();
-      tc_fence_before();
-      named_bar_sync(1, 128);
-      if (warp == 2 && lane == 0) {
-        tma_store_3d(&p.to, stg, h * D, qt * 128, b);              // rows >= Nq are clipped by the TMA unit
-        bulk_commit();
-        bulk_wait_read<0>();
-        mbar_arrive(empty_bar(s));                                  // Q / K / V of this stage may be overwritten
-      }
+      fence_async_smem();                                          // staging writes -> visible to the TMA store
+      tc_fence_before();                                           // O reads complete -> the next S MMA may overwrite the columns
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_cons);
     }
   }
 
@@ -336,34 +370,42 @@ struct AttnTcBwdParams {
 
 // Work item = one (batch, head).  Key tiles of 128 rows (MMA M), query tiles of up to 128 columns (MMA N).
 //   per (kt, qt):  S^T = K Q^T, dP^T = V dO^T  ->  TMEM           (warp 1)
-//                  P^T = 2^(S^T sl - L), dS^T = P^T (dP^T - D)  -> smem bf16   (warps 2..5, lane = key row)
+//                  P^T = 2^(S^T sl - L), dS^T = P^T (dP^T - D)  -> smem bf16   (warps 2..9: lane = key row, the two warps of a
+//                                                                 TMEM lane quadrant split the query columns)
 //                  dV[kt] += P^T dO, dK[kt] += dS^T Q, dQ[qt] += dS K         (warp 1; accumulators stay in TMEM)
 //   TMEM columns: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ tile 0 [384,448) | dQ tile 1 [448,512)
+//   warp 0 loads the operand tiles (NP = 128: two stages, the next item's tiles land while this one computes) and issues
+//   the TMA stores of the finished output tiles, so the compute warps never wait for a store.
 template <int D, int NP>
-__global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_constant__ AttnTcBwdParams p) {
+__global__ void __launch_bounds__(320, 1) attn_tc_bwd_kernel(const __grid_constant__ AttnTcBwdParams p) {
+  constexpr int STAGES = NP == 128 ? 2 : 1;
   constexpr uint32_t OP_BYTES = NP * 128;                          // one operand tile set: Q, K, V or dO
+  constexpr uint32_t STAGE_BYTES = 4 * OP_BYTES;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t C_ST = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+  constexpr int NCW = 8;                                            // compute warps
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t qs = smem_base, ks = qs + OP_BYTES, vs = ks + OP_BYTES, dos = vs + OP_BYTES;
-  const uint32_t pt_base = dos + OP_BYTES;                         // P^T  [128 keys][128 queries] bf16: 2 chunks of 64 queries
+  const uint32_t pt_base = smem_base + STAGES * STAGE_BYTES;       // P^T  [128 keys][128 queries] bf16: 2 tiles of 64 queries
   const uint32_t dst_base = pt_base + 2 * kTile;                   // dS^T, same layout
   const uint32_t ls_base = dst_base + 2 * kTile;                   // L[q] = lse * log2(e)   (f32, NP)
   const uint32_t ds_base = ls_base + NP * 4;                       // D[q] = dO_q . O_q       (f32, NP)
   const uint32_t bar_base = ds_base + NP * 4;
-  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8u, s_ready = bar_base + 16u, p_ready = bar_base + 24u,
-                 acc_ready = bar_base + 32u, tmem_ptr_addr = bar_base + 40u;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
+  const uint32_t s_ready = bar_base + 32u, p_ready = bar_base + 40u, acc_ready = bar_base + 48u, out_ready = bar_base + 56u,
+                 stg_free = bar_base + 64u, tmem_ptr_addr = bar_base + 72u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     const CUtensorMap* maps[7] = {&p.tq, &p.tk, &p.tv, &p.tdo, &p.tdq, &p.tdk, &p.tdv};
     for (int i = 0; i < 7; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(maps[i])) : "memory");
-    mbar_init(full_bar, 1);
-    mbar_init(empty_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(s_ready, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, NCW);
     mbar_init(acc_ready, 1);
+    mbar_init(out_ready, NCW);
+    mbar_init(stg_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -382,22 +424,50 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
   auto col_of = [&](int h) { return D == 64 ? h * 64 : (h >> 1) * 64; };
   auto koff_of = [&](int h) { return D == 64 ? 0u : (uint32_t)(h & 1) * 64u; };
   auto n16 = [](int n) { return (n + 15) & ~15; };
+  auto stage_of = [&](int it) { return smem_base + (uint32_t)(it % STAGES) * STAGE_BYTES; };
+  // staging tiles of the outputs alias P^T / dS^T (free between the last accumulate MMA of a key tile and the next pair)
+  const uint32_t stg_dv = pt_base, stg_dk = dst_base, stg_dq0 = pt_base + kTile, stg_dq1 = dst_base + kTile;
 
   if (warp == 0) {
-    // ===================== TMA producer (single stage: the next item's tiles follow the last MMA of this one) =====================
+    // ===================== TMA producer + output stores =====================
     const bool leader = elect_one();
-    int it = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+    auto load = [&](int w, int it) {
       const int h = w % p.H, b = w / p.H;
-      mbar_wait(empty_bar, (it & 1) ^ 1u);
+      const int s = it % STAGES;
+      mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1u);
       if (leader) {
-        mbar_expect_tx(full_bar, 4 * OP_BYTES);
-        tma_load_3d(qs, &p.tq, full_bar, col_of(h), 0, b);
-        tma_load_3d(ks, &p.tk, full_bar, col_of(h), 0, b);
-        tma_load_3d(vs, &p.tv, full_bar, col_of(h), 0, b);
-        tma_load_3d(dos, &p.tdo, full_bar, col_of(h), 0, b);
+        const uint32_t qs = stage_of(it), ks = qs + OP_BYTES, vs = ks + OP_BYTES, dos = vs + OP_BYTES;
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        tma_load_3d(qs, &p.tq, full_bar(s), col_of(h), 0, b);
+        tma_load_3d(ks, &p.tk, full_bar(s), col_of(h), 0, b);
+        tma_load_3d(vs, &p.tv, full_bar(s), col_of(h), 0, b);
+        tma_load_3d(dos, &p.tdo, full_bar(s), col_of(h), 0, b);
       }
       __syncwarp();
+    };
+    int it = 0;
+    for (int k = 0; k < STAGES; ++k)
+      if ((int)blockIdx.x + k * (int)gridDim.x < items) load(blockIdx.x + k * gridDim.x, k);
+    uint32_t out_phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+      const int h = w % p.H, b = w / p.H;
+      for (int kt = 0; kt < nkt; ++kt) {
+        mbar_wait(out_ready, out_phase);                           // dV / dK (/ dQ) staging tiles of this key tile are written
+        out_phase ^= 1u;
+        if (leader) {
+          tma_store_3d(&p.tdv, stg_dv, h * D, kt * 128, b);
+          tma_store_3d(&p.tdk, stg_dk, h * D, kt * 128, b);
+          if (kt == nkt - 1) {
+            tma_store_3d(&p.tdq, stg_dq0, h * D, 0, b);
+            if (nqt > 1) tma_store_3d(&p.tdq, stg_dq1, h * D, 128, b);
+          }
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(stg_free);
+        }
+        __syncwarp();
+      }
+      if (w + STAGES * (int)gridDim.x < items) load(w + STAGES * gridDim.x, it + STAGES);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -409,7 +479,9 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       const int h = w % p.H;
       const uint32_t koff = koff_of(h);
-      mbar_wait(full_bar, it & 1);
+      const int s = it % STAGES;
+      const uint32_t qs = stage_of(it), ks = qs + OP_BYTES, vs = ks + OP_BYTES, dos = vs + OP_BYTES;
+      mbar_wait(full_bar(s), (it / STAGES) & 1);
       tc_fence_after();
       auto issue_scores = [&](int kt, int qt) {                    // S^T and dP^T of one pair
         const uint32_t idesc_s = make_idesc(128, n16(min(128, p.Nq - qt * 128)), 0, 0);
@@ -444,72 +516,69 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
                      make_smem_desc(ks + (uint32_t)(kt * 128 + kk * 16) * 128u, 8192, 1024), idesc_dq, (kt > 0 || kk > 0) ? 1u : 0u);
           if (qt == nqt - 1) umma_commit(acc_ready);               // dV / dK of this key tile complete (last pair: dQ too)
           if (pr + 1 < npairs) { issue_scores((pr + 1) / nqt, (pr + 1) % nqt); umma_commit(s_ready); }
+          else umma_commit(empty_bar(s));                          // every read of this stage's Q / K / V / dO has retired
         }
         __syncwarp();
       }
     }
   } else {
-    // ===================== compute + epilogue warps (lane = key row of the current key tile) =====================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int tid = row;                                            // 0..127 over the four warps
+    // ===================== compute + epilogue warps =====================
+    const int quad = warp & 3;                                      // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;                               // which half of the query columns / output columns
+    const int row = quad * 32 + lane;                               // key row inside the key tile
+    const int tid = half * 128 + row;                               // 0..255 over the eight warps
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl = p.scale * kLog2eTc;
     const uint32_t sw = (uint32_t)(row & 7);
     int it = 0;
-    uint32_t pair_phase = 0, acc_phase = 0;
-    // one output tile: 64 accumulator columns of this lane's row -> (x mul) -> bf16 -> staging -> TMA store (clipped at `rows`)
-    auto store_tile = [&](uint32_t tcol, uint32_t stg, const CUtensorMap* map, float mul, int h, int row0, int b) {
+    uint32_t pair_phase = 0, acc_phase = 0, stg_phase = 0;
+    bool stg_pending = false;                                       // a TMA store of the staging tiles (= P^T / dS^T) may still be reading them
+    // this warp's half (32 columns; d = 32: 16) of one 64-column accumulator row -> (x mul) -> bf16 -> staging tile
+    auto stage_tile = [&](uint32_t tcol, uint32_t stg, float mul, int h) {
       if (D == 64) {
-        uint32_t z0[32], z1[32];
-        tmem_ld_32x32b_x32_issue(trow + tcol, z0);
-        tmem_ld_32x32b_x32_issue(trow + tcol + 32, z1);
-        tmem_ld_wait(z0);
-        tmem_ld_wait(z1);
+        uint32_t z[32];
+        tmem_ld_32x32b_x32_issue(trow + tcol + (uint32_t)half * 32u, z);
+        tmem_ld_wait(z);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t* z = j < 4 ? z0 + 8 * j : z1 + 8 * (j - 4);
-          sts_128(stg + (uint32_t)row * 128u + (((uint32_t)j ^ sw) << 4),
-                  pack_bf16x2(__uint_as_float(z[0]) * mul, __uint_as_float(z[1]) * mul), pack_bf16x2(__uint_as_float(z[2]) * mul, __uint_as_float(z[3]) * mul),
-                  pack_bf16x2(__uint_as_float(z[4]) * mul, __uint_as_float(z[5]) * mul), pack_bf16x2(__uint_as_float(z[6]) * mul, __uint_as_float(z[7]) * mul));
-        }
+        for (int j = 0; j < 4; ++j)
+          sts_128(stg + (uint32_t)row * 128u + ((((uint32_t)half * 4u + j) ^ sw) << 4),
+                  pack_bf16x2(__uint_as_float(z[8 * j]) * mul, __uint_as_float(z[8 * j + 1]) * mul), pack_bf16x2(__uint_as_float(z[8 * j + 2]) * mul, __uint_as_float(z[8 * j + 3]) * mul),
+                  pack_bf16x2(__uint_as_float(z[8 * j + 4]) * mul, __uint_as_float(z[8 * j + 5]) * mul), pack_bf16x2(__uint_as_float(z[8 * j + 6]) * mul, __uint_as_float(z[8 * j + 7]) * mul));
       } else {
-        uint32_t z0[32];
-        tmem_ld_32x32b_x32_issue(trow + tcol + (uint32_t)(h & 1) * 32u, z0);
-        tmem_ld_wait(z0);
+        float z[16];
+        tmem_ld_32x32b_x16(trow + tcol + (uint32_t)(h & 1) * 32u + (uint32_t)half * 16u, z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t* z = z0 + 8 * j;
-          sts_128(stg + (uint32_t)row * 64u + ((uint32_t)j << 4),
-                  pack_bf16x2(__uint_as_float(z[0]) * mul, __uint_as_float(z[1]) * mul), pack_bf16x2(__uint_as_float(z[2]) * mul, __uint_as_float(z[3]) * mul),
-                  pack_bf16x2(__uint_as_float(z[4]) * mul, __uint_as_float(z[5]) * mul), pack_bf16x2(__uint_as_float(z[6]) * mul, __uint_as_float(z[7]) * mul));
-        }
-      }
-      fence_async_smem();
-      tc_fence_before();
-      named_bar_sync(1, 128);
-      if (warp == 2 && lane == 0) {
-        tma_store_3d(map, stg, h * D, row0, b);
-        bulk_commit();
+        for (int j = 0; j < 2; ++j)
+          sts_128(stg + (uint32_t)row * 64u + (((uint32_t)half * 2u + j) << 4),
+                  pack_bf16x2(z[8 * j] * mul, z[8 * j + 1] * mul), pack_bf16x2(z[8 * j + 2] * mul, z[8 * j + 3] * mul),
+                  pack_bf16x2(z[8 * j + 4] * mul, z[8 * j + 5] * mul), pack_bf16x2(z[8 * j + 6] * mul, z[8 * j + 7] * mul));
       }
     };
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
       const int h = w % p.H, b = w / p.H;
       const uint32_t koff = koff_of(h);
-      mbar_wait(full_bar, it & 1);
-      // ---- L[q] and D[q] = dO_q . O_q for every query of the head (thread per query row) ----
-      for (int q = tid; q < NP; q += 128) {
-        float Lq = 1e30f, Dq = 0.f;                                  // padded queries: P = 2^(-inf) = 0, dS = 0
-        if (q < p.Nq) {
-          Lq = p.lse[((int64_t)b * p.H + h) * p.Nq + q] * kLog2eTc;
-          const uint16_t* orow = p.o + (int64_t)b * p.o_bs + (int64_t)q * p.o_rs + (int64_t)h * D;
-          const uint32_t drow = dos + (uint32_t)q * 128u;
-          const uint32_t qsw = (uint32_t)(q & 7);
+      const uint32_t dos = stage_of(it) + 3 * OP_BYTES;
+      // ---- L[q] and D[q] = dO_q . O_q for every query of the head (thread per query row); the forward output row is
+      //      fetched from global memory before the wait on the operand tiles ----
+      uint4 orow[D / 8];
+      const bool have_q = tid < p.Nq;
+      float Lq = 1e30f;                                              // padded queries: P = 2^(-inf) = 0, dS = 0
+      if (have_q) {
+        const uint16_t* op = p.o + (int64_t)b * p.o_bs + (int64_t)tid * p.o_rs + (int64_t)h * D;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) orow[j] = *reinterpret_cast<const uint4*>(op + 8 * j);
+        Lq = p.lse[((int64_t)b * p.H + h) * p.Nq + tid] * kLog2eTc;
+      }
+      mbar_wait(full_bar(it % STAGES), (it / STAGES) & 1);
+      if (tid < NP) {
+        float Dq = 0.f;
+        if (have_q) {
+          const uint32_t drow = dos + (uint32_t)tid * 128u;
+          const uint32_t qsw = (uint32_t)(tid & 7);
 #pragma unroll
           for (int j = 0; j < D / 8; ++j) {
-            const uint4 xo = *reinterpret_cast<const uint4*>(orow + 8 * j);
             const uint4 yo = lds_128(drow + ((((koff >> 4) + (uint32_t)j) ^ qsw) << 4));
-            const uint32_t xs[4] = {xo.x, xo.y, xo.z, xo.w}, ys[4] = {yo.x, yo.y, yo.z, yo.w};
+            const uint32_t xs[4] = {orow[j].x, orow[j].y, orow[j].z, orow[j].w}, ys[4] = {yo.x, yo.y, yo.z, yo.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 x = unpack_bf16x2(xs[e]), y = unpack_bf16x2(ys[e]);
@@ -517,10 +586,10 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
             }
           }
         }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ls_base + 4u * q), "f"(Lq) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ds_base + 4u * q), "f"(Dq) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ls_base + 4u * tid), "f"(Lq) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ds_base + 4u * tid), "f"(Dq) : "memory");
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, NCW * 32);
       for (int pr = 0; pr < npairs; ++pr) {
         const int kt = pr / nqt, qt = pr % nqt;
         const int nq_t = n16(min(128, p.Nq - qt * 128));
@@ -528,8 +597,10 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
         mbar_wait(s_ready, pair_phase);
         pair_phase ^= 1u;
         tc_fence_after();
-        // s_ready also tells that the accumulate MMAs of the previous pair have retired: P^T / dS^T may be overwritten
-        for (int c = 0; c < nq_t; c += 32) {
+        // s_ready also tells that the accumulate MMAs of the previous pair have retired: P^T / dS^T may be overwritten --
+        // once the TMA stores that used them as staging tiles have read them
+        if (stg_pending) { mbar_wait(stg_free, stg_phase); stg_phase ^= 1u; stg_pending = false; }
+        for (int c = half * 32; c < nq_t; c += 64) {               // the two warps of a lane quadrant alternate 32-column chunks
           uint32_t sv[32], dv[32];
           tmem_ld_32x32b_x32_issue(trow + C_ST + c, sv);
           tmem_ld_32x32b_x32_issue(trow + C_DP + c, dv);
@@ -563,23 +634,26 @@ __global__ void __launch_bounds__(192, 1) attn_tc_bwd_kernel(const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
         if (qt == nqt - 1) {
-          // ---- dV / dK of this key tile (and, after the last one, dQ): every MMA issued so far has retired ----
+          // ---- dV / dK of this key tile (and, after the last one, dQ): every MMA issued so far has retired, so the
+          //      accumulators are final and P^T / dS^T are free to serve as staging tiles ----
           mbar_wait(acc_ready, acc_phase);
           acc_phase ^= 1u;
           tc_fence_after();
-          // staging tiles alias P^T / dS^T: free (their readers have retired) until the next pair's s_ready
-          store_tile(C_DV, pt_base, &p.tdv, 1.0f, h, kt * 128, b);
-          store_tile(C_DK, dst_base, &p.tdk, p.scale, h, kt * 128, b);
+          stage_tile(C_DV, stg_dv, 1.0f, h);
+          stage_tile(C_DK, stg_dk, p.scale, h);
           if (kt == nkt - 1) {
-            for (int t = 0; t < nqt; ++t) store_tile(C_DQ + t * 64, (t == 0 ? pt_base : dst_base) + kTile, &p.tdq, p.scale, h, t * 128, b);
+            stage_tile(C_DQ, stg_dq0, p.scale, h);
+            if (nqt > 1) stage_tile(C_DQ + 64, stg_dq1, p.scale, h);
           }
-          if (warp == 2 && lane == 0) bulk_wait_read<0>();          // the staging tiles are about to be overwritten
+          fence_async_smem();
           tc_fence_before();
-          named_bar_sync(1, 128);
-          if (kt == nkt - 1 && warp == 2 && lane == 0) mbar_arrive(empty_bar);     // Q / K / V / dO may be overwritten
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_ready);                    // warp 0 issues the TMA stores
+          stg_pending = true;
         }
       }
     }
+    if (stg_pending) mbar_wait(stg_free, stg_phase);                // (keeps the CTA alive until its last stores have read shared memory)
   }
 
   __syncwarp();
@@ -627,8 +701,8 @@ static int launch_tc_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
   if ((rc = get_map3(a.v, cols, a.Nk, a.B, a.v_rs, a.v_bs, 64, NKP, &p.tv))) return rc;
   if ((rc = get_map3(a.o, cols, a.Nq, a.B, a.o_rs, a.o_bs, D, 128, &p.to))) return rc;
   p.lse = a.lse; p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.scale = a.scale;
-  constexpr size_t smem = 2 * (size_t)(kTile + 2 * NKP * 128) + (size_t)(NKP / 64) * kTile + 64 + 1024;
-  static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
+  constexpr size_t smem = 2 * (size_t)kTile + 2 * (size_t)NKP * 128 + 64 + 1024;      // Q | K | X | V (+ barriers, alignment slack)
+  static_assert(2 * (smem + 1024) <= 233472, "two CTAs per SM must fit the 228 KB shared memory");
   auto kern = attn_tc_fwd_kernel<D, NKP>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -636,7 +710,7 @@ static int launch_tc_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
     attr_set = true;
   }
   const int items = a.B * a.H * ((a.Nq + 127) / 128);
-  const int grid = items < kNumSMs ? items : kNumSMs;
+  const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;        // two resident CTAs per SM
   kern<<<grid, 192, smem, st>>>(p);
   g_launch_kind[kKindAttnTc].fetch_add(1);
   DAVF_LAUNCH_OK();
@@ -657,7 +731,7 @@ static int launch_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   if ((rc = get_map3(a.dv_, cols, a.Nk, a.B, a.dv_rs, a.dv_bs, D, 128, &p.tdv))) return rc;
   p.lse = a.lse; p.o = a.o; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.scale = a.scale;
-  constexpr size_t smem = 4 * (size_t)NP * 128 + 4 * (size_t)kTile + 2 * (size_t)NP * 4 + 64 + 1024;
+  constexpr size_t smem = (NP == 128 ? 2 : 1) * 4 * (size_t)NP * 128 + 4 * (size_t)kTile + 2 * (size_t)NP * 4 + 128 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   auto kern = attn_tc_bwd_kernel<D, NP>;
   static bool attr_set = false;
@@ -667,7 +741,7 @@ static int launch_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   }
   const int items = a.B * a.H;
   const int grid = items < kNumSMs ? items : kNumSMs;
-  kern<<<grid, 192, smem, st>>>(p);
+  kern<<<grid, 320, smem, st>>>(p);
   g_launch_kind[kKindAttnTc].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;

@@ -74,11 +74,17 @@ def ln(B, n0, n1, D, tag):
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
-    attn(64, 12, 81, 32, 64, "enc image")
-    attn(64, 12, 51, 32, 64, "enc audio")
-    attn(64, 16, 228, 0, 32, "dec image")
-    attn(64, 16, 128, 0, 32, "dec audio")
-    attn(64, 12, 49, 41, 64, "cross v (8q)")
+    for impl, name in ((0, "tcgen05 (product dispatch)"), (2, "mma.sync everywhere")):
+        K.set_attn_impl(impl)
+        print(f"--- attention impl {impl}: {name}")
+        attn(64, 12, 81, 32, 64, "enc image")
+        attn(64, 12, 51, 32, 64, "enc audio")
+        attn(64, 16, 228, 0, 32, "dec image")
+        attn(64, 16, 128, 0, 32, "dec audio")
+        attn(32, 12, 228, 32, 64, "enc image full")
+        attn(32, 12, 128, 32, 64, "enc audio full")
+        attn(64, 12, 49, 41, 64, "cross v (8q)")
+    K.set_attn_impl(0)
     ln(64, 32, 49, 768, "enc image")
     ln(64, 49, 0, 768, "enc image mlp")
     ln(64, 228, 0, 512, "dec image")

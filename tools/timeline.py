@@ -7,8 +7,9 @@ import torch
 import bench
 from deepavfusion_b200.util.graphed import GraphedTrainStep
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
-trainer = bench.build_trainer(dev, False)
-img, aud = bench.synth_inputs(64, 1000, False)
+CFG = bench.CONFIGS[os.environ.get("DAVF_BENCH_CONFIG", "vggsound")]
+trainer = bench.build_trainer(CFG, dev, False)
+img, aud = bench.synth_inputs(CFG, CFG["batch"], 1000, False)[:2]
 img, aud = img.to(dev), aud.to(dev)
 def _eager():
     li, la, _, _ = trainer.model(img, aud); trainer.step(li + la)
@@ -48,6 +49,10 @@ def first(name):
 out.append(f"loss bwd starts at {first('masked_mse_kernel<true>')} ms, adamw at {first('adamw_kernel')} ms")
 agg = collections.defaultdict(float)
 for e in ks: agg[e["name"][:60]] += e["dur"]
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:14]: out.append(f"{v / 1e3:8.2f} ms  {k}")
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:24]: out.append(f"{v / 1e3:8.2f} ms  {k}")
+# the head of the step: the first kernels and the gaps between them
+out.append("first 40 kernels (start ms, dur us, stream, name):")
+for e in ks[:40]: out.append(f"  {(e['ts'] - t0) / 1e3:7.3f} {e['dur']:7.1f} {e['args'].get('stream')} {e['name'][:70]}")
+out.append(f"sum of kernel time {sum(e['dur'] for e in ks) / 1e3:.2f} ms")
 open("gpurun_out/timeline_summary.txt", "w").write("\n".join(out))
 print("\n".join(out))
