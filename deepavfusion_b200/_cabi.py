@@ -73,7 +73,7 @@ class AttnBwdArgs(C.Structure):
                 ("dv_", vp), ("dv_bs", C.c_int64), ("dv_rs", C.c_int64),
                 ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dqk", C.c_int), ("dv", C.c_int),
                 ("scale", C.c_float), ("accumulate_dq", C.c_int),
-                ("o", vp), ("o_bs", C.c_int64), ("o_rs", C.c_int64)]
+                ("o", vp), ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("dq_dead_rows", C.c_int)]
 
 
 i, i64, f = C.c_int, C.c_int64, C.c_float
@@ -90,9 +90,11 @@ SIGNATURES = {
     "davf_set_attn_impl": (i, [i]),
     "davf_launch_count": (i64, []),
     "davf_launch_count_kind": (i64, [i]),
+    "davf_set_pdl": (i, [i]),
     "davf_mask_rank": (i, [vp, i, i, i, vp, vp, vp, vp]),
     "davf_patch_rows": (i, [vp, vp, vp, i, i, i, i, i, i, vp]),
     "davf_cast_rows_bf16": (i, [vp, vp, i64, i, i, i, i, vp]),
+    "davf_sum_cast": (i, [vp, vp, vp, vp, vp, i64, vp]),
     "davf_colsum_bf16": (i, [vp, i64, i, i64, vp, vp]),
     "davf_batchsum_f32": (i, [vp, i, i, i, i, i, vp, i, vp]),
     "davf_layernorm_fwd": (i, [C.POINTER(LnFwdArgs), vp]),

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, floa
                                                     const uint8_t* __restrict__ chunk_group, const float* __restrict__ hp,
                                                     const float* __restrict__ scal, float beta1, float beta2, float eps,
                                                     int zero_grad, float* __restrict__ sumsq_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float scratch[32];
   const float bc1 = 1.0f - scal[0], bc2 = 1.0f - scal[1], gsc = scal[2];
   const float inv_sqrt_bc2 = rsqrtf(bc2);
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, floa
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, int64_t n4, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float scratch[32];
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -80,9 +84,9 @@ extern "C" int davf_adamw_step(float* p, float* g, float* m, float* v, davf_bf16
   if (n == 0) return DAVF_OK;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-  adamw_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
+  DAVF_CUDA(launch_pdl(adamw_kernel, dim3((int)blocks), dim3(256), 0, as_stream(s), reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
                                                      reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p_bf16), n / 4, chunk_group, hp,
-                                                     scal, beta1, beta2, eps, zero_grad, sumsq_out);
+                                                     scal, beta1, beta2, eps, zero_grad, sumsq_out));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -92,7 +96,7 @@ extern "C" int davf_sumsq_f32(const float* g, int64_t n, float* out, davf_stream
   if (n == 0) return DAVF_OK;
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  sumsq_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(g), n / 4, out);
+  DAVF_CUDA(launch_pdl(sumsq_kernel, dim3((int)blocks), dim3(256), 0, as_stream(s), reinterpret_cast<const float4*>(g), n / 4, out));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

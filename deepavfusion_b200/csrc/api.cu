@@ -1,11 +1,13 @@
 // Library plumbing: error string, version, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace davf {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int64_t> g_launch_kind[kNumKinds];
+std::atomic<int> g_pdl{[] { const char* e = getenv("DAVF_PDL"); return e ? atoi(e) : 0; }()};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -25,6 +27,7 @@ int davf_device_sm(void) {
   return major * 10 + minor;
 }
 int64_t davf_launch_count(void) { return davf::g_launches.load(); }
+int davf_set_pdl(int on) { davf::g_pdl.store(on ? 1 : 0); return DAVF_OK; }
 int64_t davf_launch_count_kind(int kind) {
   if (kind <= 0 || kind >= davf::kNumKinds) return davf::g_launches.load();
   return davf::g_launch_kind[kind].load();

@@ -114,6 +114,18 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+
+// o (+)= (x, y) as one packed bf16 pair.  mode 0: store; 1: read-modify-write (the caller orders the launches that add into
+// the same buffer); 2: red.global.add.bf16x2 -- launches that add into the same (zero-initialised) buffer may run concurrently
+__device__ __forceinline__ void put_pair(uint32_t* p, float x, float y, int mode) {
+  if (mode == 2) {
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(x, y));
+    return;
+  }
+  if (mode == 1) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
+  *p = pack_bf16x2(x, y);
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -122,6 +134,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 // ---------------------------------------------------------------------------------------------
 template <int DQK, int DV, int NW>
 __global__ void __launch_bounds__(NW * 32) attn_mma_fwd_kernel(davf_attn_fwd_args a, int Nkp) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int QT = NW * 16;                                  // query rows per CTA
   uint16_t* Qs = reinterpret_cast<uint16_t*>(smem);            // [QT][DQK+8]
@@ -197,15 +211,11 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_fwd_kernel(davf_attn_fwd_arg
     const int col = nt * 8 + 2 * t;
     if (r0 < a.Nq) {
       uint32_t* p = reinterpret_cast<uint32_t*>(ob + (int64_t)r0 * a.o_rs + col);
-      float x = o[nt][0] * il0, y = o[nt][1] * il0;
-      if (a.accumulate) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
-      *p = pack_bf16x2(x, y);
+      put_pair(p, o[nt][0] * il0, o[nt][1] * il0, a.accumulate);
     }
     if (r1 < a.Nq) {
       uint32_t* p = reinterpret_cast<uint32_t*>(ob + (int64_t)r1 * a.o_rs + col);
-      float x = o[nt][2] * il1, y = o[nt][3] * il1;
-      if (a.accumulate) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
-      *p = pack_bf16x2(x, y);
+      put_pair(p, o[nt][2] * il1, o[nt][3] * il1, a.accumulate);
     }
   }
   if (a.lse && t == 0) {
@@ -223,6 +233,8 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_fwd_kernel(davf_attn_fwd_arg
 // ---------------------------------------------------------------------------------------------
 template <int DQK, int DV, int NW>
 __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_args a, int Nqp, int Nkp) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   uint16_t* Qs = reinterpret_cast<uint16_t*>(smem);            // [Nqp][DQK+8]
   uint16_t* Ks = Qs + Nqp * (DQK + 8);                         // [Nkp][DQK+8]
@@ -317,15 +329,11 @@ __global__ void __launch_bounds__(NW * 32) attn_mma_bwd_kernel(davf_attn_bwd_arg
           const int col = nt * 8 + 2 * t;
           if (r0 < Nq) {
             uint32_t* p = reinterpret_cast<uint32_t*>(qb + (int64_t)r0 * a.dq_rs + col);
-            float x = dq[nt][0] * a.scale, y = dq[nt][1] * a.scale;
-            if (a.accumulate_dq) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
-            *p = pack_bf16x2(x, y);
+            put_pair(p, dq[nt][0] * a.scale, dq[nt][1] * a.scale, a.accumulate_dq);
           }
           if (r1 < Nq) {
             uint32_t* p = reinterpret_cast<uint32_t*>(qb + (int64_t)r1 * a.dq_rs + col);
-            float x = dq[nt][2] * a.scale, y = dq[nt][3] * a.scale;
-            if (a.accumulate_dq) { const float2 old = unpack_bf16x2(*p); x += old.x; y += old.y; }
-            *p = pack_bf16x2(x, y);
+            put_pair(p, dq[nt][2] * a.scale, dq[nt][3] * a.scale, a.accumulate_dq);
           }
         }
       }
@@ -400,7 +408,7 @@ static int launch_fwd_nw(const davf_attn_fwd_args& a, cudaStream_t st) {
     configured = smem;
   }
   dim3 grid((a.Nq + QT - 1) / QT, a.B * a.H);
-  kern<<<grid, NW * 32, smem, st>>>(a, Nkp);
+  DAVF_CUDA(launch_pdl(kern, grid, dim3(NW * 32), smem, st, a, Nkp));
   g_launch_kind[kKindAttnMma].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
@@ -430,7 +438,7 @@ static int launch_bwd_nw(const davf_attn_bwd_args& a, cudaStream_t st) {
     DAVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
-  kern<<<a.B * a.H, NW * 32, smem, st>>>(a, Nqp, Nkp);
+  DAVF_CUDA(launch_pdl(kern, dim3(a.B * a.H), dim3(NW * 32), smem, st, a, Nqp, Nkp));
   g_launch_kind[kKindAttnMma].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
@@ -453,6 +461,28 @@ int attn_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st);
 static std::atomic<int> g_attn_impl{0};
 
 static bool s8(int64_t x) { return x % 8 == 0; }
+
+// dq_dead_rows for the kernels that do not zero-fill themselves: [B][dead][cols] bf16 pairs in front of dq
+__global__ void attn_zero_dead_kernel(uint16_t* dq, int64_t bs, int64_t rs, int B, int dead, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int per_row = cols / 2;
+  const int64_t total = (int64_t)B * dead * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % per_row);
+    const int64_t r = i / per_row;
+    const int row = (int)(r % dead);
+    const int64_t b = r / dead;
+    *reinterpret_cast<uint32_t*>(dq + b * bs + (int64_t)(row - dead) * rs + 2 * c) = 0u;
+  }
+}
+static int zero_dead_rows(const davf_attn_bwd_args& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.B * a.dq_dead_rows * (a.H * a.dqk / 2);
+  const int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+  DAVF_CUDA(launch_pdl(attn_zero_dead_kernel, dim3(grid), dim3(256), 0, st, a.dq, a.dq_bs, a.dq_rs, a.B, a.dq_dead_rows, a.H * a.dqk));
+  DAVF_LAUNCH_OK();
+  return DAVF_OK;
+}
 
 }  // namespace davf
 
@@ -489,10 +519,13 @@ extern "C" int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s) 
   DAVF_CHECK_ARG((((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v | (uintptr_t)a->d_o) & 15) == 0, "attention_bwd: q/k/v/dO must be 16-byte aligned");
   DAVF_CHECK_ARG(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0 && a->dq_bs % 2 == 0 && a->dk_bs % 2 == 0 && a->dv_bs % 2 == 0,
                  "attention_bwd: gradient strides must be even");
+  DAVF_CHECK_ARG(a->dq_dead_rows >= 0 && a->dq_dead_rows <= 4096, "attention_bwd: dq_dead_rows=%d", a->dq_dead_rows);
   if (a->B == 0) return DAVF_OK;
   cudaStream_t st = as_stream(s);
+  if (g_attn_impl.load() == 0 && attn_tc_bwd_ok(*a)) return attn_tc_bwd(*a, st);     // (zero-fills the dead rows itself)
+  if (a->dq_dead_rows > 0)
+    if (int rc = zero_dead_rows(*a, st)) return rc;
   if (g_attn_impl.load() == 1) return attn_simt_bwd(a, st);
-  if (g_attn_impl.load() == 0 && attn_tc_bwd_ok(*a)) return attn_tc_bwd(*a, st);
   if (a->dqk == 64 && a->dv == 64) return launch_bwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_bwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_bwd<16, 64>(*a, st);

@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(192, 2) attn_tc_fwd_kernel(const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  pdl_launch_dependents();     // set-up done, nothing global touched yet (PDL, common.cuh)
+  pdl_wait();
 
   const int nqt = (p.Nq + 127) >> 7;
   const int items = p.B * p.H * nqt;
@@ -362,6 +364,8 @@ __global__ void __launch_bounds__(192, 2) attn_tc_fwd_kernel(const __grid_consta
 struct AttnTcBwdParams {
   CUtensorMap tq, tk, tv, tdo;          // loads: box {64, NP, 1}
   CUtensorMap tdq, tdk, tdv;            // stores: box {D, 128, 1}
+  CUtensorMap tdq0;                     // the dead query rows in front of dq (zero-filled): box {D, 32, 1}
+  int dead;
   const float* lse;
   const uint16_t* o; int64_t o_bs, o_rs;
   int B, H, Nq, Nk;
@@ -390,7 +394,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_bwd_kernel(const __grid_consta
   const uint32_t dst_base = pt_base + 2 * kTile;                   // dS^T, same layout
   const uint32_t ls_base = dst_base + 2 * kTile;                   // L[q] = lse * log2(e)   (f32, NP)
   const uint32_t ds_base = ls_base + NP * 4;                       // D[q] = dO_q . O_q       (f32, NP)
-  const uint32_t bar_base = ds_base + NP * 4;
+  const uint32_t zero_base = ds_base + NP * 4;                     // [32 rows][128 B] of zeros: source of the dead-row stores
+  const uint32_t bar_base = zero_base + 4096;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
   const uint32_t s_ready = bar_base + 32u, p_ready = bar_base + 40u, acc_ready = bar_base + 48u, out_ready = bar_base + 56u,
@@ -412,11 +417,17 @@ __global__ void __launch_bounds__(320, 1) attn_tc_bwd_kernel(const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) {
+    for (uint32_t i = threadIdx.x - 64; i < 4096 / 16; i += NCW * 32) sts_128(zero_base + 16u * i, 0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  pdl_launch_dependents();     // set-up done, nothing global touched yet (PDL, common.cuh)
+  pdl_wait();
 
   const int items = p.B * p.H;
   const int nqt = (p.Nq + 127) >> 7, nkt = (p.Nk + 127) >> 7;
@@ -455,6 +466,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_bwd_kernel(const __grid_consta
         mbar_wait(out_ready, out_phase);                           // dV / dK (/ dQ) staging tiles of this key tile are written
         out_phase ^= 1u;
         if (leader) {
+          if (kt == 0)
+            for (int r0 = 0; r0 < p.dead; r0 += 32) tma_store_3d(&p.tdq0, zero_base, h * D, r0, b);      // dead query slots := 0
           tma_store_3d(&p.tdv, stg_dv, h * D, kt * 128, b);
           tma_store_3d(&p.tdk, stg_dk, h * D, kt * 128, b);
           if (kt == nkt - 1) {
@@ -711,7 +724,7 @@ static int launch_tc_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
   }
   const int items = a.B * a.H * ((a.Nq + 127) / 128);
   const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;        // two resident CTAs per SM
-  kern<<<grid, 192, smem, st>>>(p);
+  DAVF_CUDA(launch_pdl(kern, dim3(grid), dim3(192), smem, st, p));
   g_launch_kind[kKindAttnTc].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;
@@ -729,9 +742,13 @@ static int launch_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   if ((rc = get_map3(a.dq, cols, a.Nq, a.B, a.dq_rs, a.dq_bs, D, 128, &p.tdq))) return rc;
   if ((rc = get_map3(a.dk, cols, a.Nk, a.B, a.dk_rs, a.dk_bs, D, 128, &p.tdk))) return rc;
   if ((rc = get_map3(a.dv_, cols, a.Nk, a.B, a.dv_rs, a.dv_bs, D, 128, &p.tdv))) return rc;
+  p.dead = a.dq_dead_rows;
+  p.tdq0 = p.tdq;
+  if (a.dq_dead_rows > 0 &&
+      (rc = get_map3(a.dq - (int64_t)a.dq_dead_rows * a.dq_rs, cols, a.dq_dead_rows, a.B, a.dq_rs, a.dq_bs, D, 32, &p.tdq0))) return rc;
   p.lse = a.lse; p.o = a.o; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
   p.B = a.B; p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk; p.scale = a.scale;
-  constexpr size_t smem = (NP == 128 ? 2 : 1) * 4 * (size_t)NP * 128 + 4 * (size_t)kTile + 2 * (size_t)NP * 4 + 128 + 1024;
+  constexpr size_t smem = (NP == 128 ? 2 : 1) * 4 * (size_t)NP * 128 + 4 * (size_t)kTile + 2 * (size_t)NP * 4 + 4096 + 128 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   auto kern = attn_tc_bwd_kernel<D, NP>;
   static bool attr_set = false;
@@ -741,7 +758,7 @@ static int launch_tc_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   }
   const int items = a.B * a.H;
   const int grid = items < kNumSMs ? items : kNumSMs;
-  kern<<<grid, 320, smem, st>>>(p);
+  DAVF_CUDA(launch_pdl(kern, dim3(grid), dim3(320), smem, st, p));
   g_launch_kind[kKindAttnTc].fetch_add(1);
   DAVF_LAUNCH_OK();
   return DAVF_OK;

@@ -42,6 +42,37 @@ extern std::atomic<int64_t> g_launch_kind[kNumKinds];
 
 static inline cudaStream_t as_stream(davf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The step is ~1,200 kernel launches averaging < 20 us on a handful of streams, so the per-launch fixed cost (launch
+// latency, barrier init, TMEM allocation, tensor-map prefetch) is a double-digit share of it.  Every hot kernel therefore
+// (1) executes griddepcontrol.launch_dependents first, which lets the NEXT kernel of its stream be scheduled as soon as SM
+// resources free up, and (2) executes griddepcontrol.wait before its first global-memory access, which blocks until the
+// previous kernel has completed and its writes are visible -- so a kernel's set-up overlaps its predecessor's tail while
+// every memory dependency (RAW and WAR: nothing is read or written before the wait) is ordered exactly as without PDL.
+// Launches carry cudaLaunchAttributeProgrammaticStreamSerialization; stream capture turns it into programmatic graph edges.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Measured on B200 (profiles/r2): with the step's three-to-five concurrent streams PDL LOSES 2 % (16.55 -> 16.86 ms) -- a dependent
+// kernel whose CTAs become resident early holds its SMs' shared memory while it waits, and those SMs are then not available to
+// the READY kernels of the other streams.  The step is bound by the SM-exclusive time of the big kernels, not by launch
+// latency.  The attribute is therefore OFF by default (davf_set_pdl(1) / DAVF_PDL=1 turns it on: single-stream callers).
+extern std::atomic<int> g_pdl;
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 constexpr int kNumSMs = 148;
 
 __device__ __forceinline__ float warp_sum(float v) {

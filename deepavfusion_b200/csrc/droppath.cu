@@ -9,6 +9,8 @@ namespace davf {
 
 __global__ void scale_rows_add_kernel(const float4* __restrict__ res, const float4* __restrict__ y, const float* __restrict__ scale,
                                       int rps, int64_t rows, int D4, float4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n = rows * D4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float s = scale[(i / D4) / rps];
@@ -19,6 +21,8 @@ __global__ void scale_rows_add_kernel(const float4* __restrict__ res, const floa
 
 __global__ void scale_rows_kernel(const float4* __restrict__ src, const float* __restrict__ scale, int rps, int64_t rows, int D4,
                                   float4* __restrict__ dst_f32, uint2* __restrict__ dst_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n = rows * D4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float s = scale[(i / D4) / rps];
@@ -49,8 +53,8 @@ extern "C" int davf_scale_rows_add(const float* res, const float* y, const float
   DAVF_CHECK_ARG(res && y && scale && out && rows >= 0 && rows_per_sample > 0 && D > 0 && D % 4 == 0, "scale_rows_add: bad argument");
   DAVF_CHECK_ARG(rows % rows_per_sample == 0, "scale_rows_add: rows=%lld is not a multiple of rows_per_sample=%d", (long long)rows, rows_per_sample);
   if (rows == 0) return DAVF_OK;
-  scale_rows_add_kernel<<<grid_1d(rows * (D / 4)), 256, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(y),
-                                                                          scale, rows_per_sample, rows, D / 4, reinterpret_cast<float4*>(out));
+  DAVF_CUDA(launch_pdl(scale_rows_add_kernel, dim3(grid_1d(rows * (D / 4))), dim3(256), 0, as_stream(s), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(y),
+                                                                          scale, rows_per_sample, rows, D / 4, reinterpret_cast<float4*>(out)));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -60,8 +64,8 @@ extern "C" int davf_scale_rows(const float* src, const float* scale, int rows_pe
   DAVF_CHECK_ARG(src && scale && (dst_f32 || dst_bf16) && rows >= 0 && rows_per_sample > 0 && D > 0 && D % 4 == 0, "scale_rows: bad argument");
   DAVF_CHECK_ARG(rows % rows_per_sample == 0, "scale_rows: rows=%lld is not a multiple of rows_per_sample=%d", (long long)rows, rows_per_sample);
   if (rows == 0) return DAVF_OK;
-  scale_rows_kernel<<<grid_1d(rows * (D / 4)), 256, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(src), scale, rows_per_sample, rows, D / 4,
-                                                                      reinterpret_cast<float4*>(dst_f32), reinterpret_cast<uint2*>(dst_bf16));
+  DAVF_CUDA(launch_pdl(scale_rows_kernel, dim3(grid_1d(rows * (D / 4))), dim3(256), 0, as_stream(s), reinterpret_cast<const float4*>(src), scale, rows_per_sample, rows, D / 4,
+                                                                      reinterpret_cast<float4*>(dst_f32), reinterpret_cast<uint2*>(dst_bf16)));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

@@ -205,6 +205,10 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote arrive / TMA
   tc_fence_after();
+  // set-up done (barriers, TMEM, descriptor prefetch: nothing global was touched): let the next kernel of the stream start
+  // its own set-up, then wait until the previous kernel's results are visible (see common.cuh, PDL)
+  pdl_launch_dependents();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
@@ -684,13 +688,22 @@ static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl.load(std::memory_order_relaxed)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CG > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   DAVF_CUDA(cudaLaunchKernelEx(&cfg, kern, gp));
   g_launches.fetch_add(1);
   if (CG == 2) g_launch_kind[kKindGemm2Cta].fetch_add(1);

@@ -24,6 +24,8 @@ struct RowMap {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(davf_ln_fwd_args a, RowMap rm, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float inv_d = 1.0f / (float)a.D;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(davf_ln_fwd_args a, RowMap 
 // flight per SM.  gamma is re-read through L1 per row instead of living in 4 VEC registers.
 template <int VEC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(davf_ln_bwd_args a, RowMap rm, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float sm_red[];   // [warps][2*D] : per-warp dgamma | dbeta partials
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -206,11 +210,11 @@ extern "C" int davf_layernorm_fwd(const davf_ln_fwd_args* a, davf_stream_t s) {
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
   cudaStream_t st = as_stream(s);
   switch (a->D / 128) {
-    case 4: ln_fwd_kernel<4><<<(int)blocks, 256, 0, st>>>(*a, rm, rows); break;
-    case 6: ln_fwd_kernel<6><<<(int)blocks, 256, 0, st>>>(*a, rm, rows); break;
-    case 8: ln_fwd_kernel<8><<<(int)blocks, 256, 0, st>>>(*a, rm, rows); break;
-    case 1: ln_fwd_kernel<1><<<(int)blocks, 256, 0, st>>>(*a, rm, rows); break;
-    case 2: ln_fwd_kernel<2><<<(int)blocks, 256, 0, st>>>(*a, rm, rows); break;
+    case 4: DAVF_CUDA(launch_pdl(ln_fwd_kernel<4>, dim3((int)blocks), dim3(256), 0, st, *a, rm, rows)); break;
+    case 6: DAVF_CUDA(launch_pdl(ln_fwd_kernel<6>, dim3((int)blocks), dim3(256), 0, st, *a, rm, rows)); break;
+    case 8: DAVF_CUDA(launch_pdl(ln_fwd_kernel<8>, dim3((int)blocks), dim3(256), 0, st, *a, rm, rows)); break;
+    case 1: DAVF_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3((int)blocks), dim3(256), 0, st, *a, rm, rows)); break;
+    case 2: DAVF_CUDA(launch_pdl(ln_fwd_kernel<2>, dim3((int)blocks), dim3(256), 0, st, *a, rm, rows)); break;
     default:
       set_error("layernorm_fwd: D=%d not instantiated", a->D);
       return DAVF_EUNSUPPORTED;
@@ -246,11 +250,11 @@ extern "C" int davf_layernorm_bwd(const davf_ln_bwd_args* a, davf_stream_t s) {
     attr_set = true;
   }
   switch (a->D / 128) {
-    case 4: ln_bwd_kernel<4><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
-    case 6: ln_bwd_kernel<6><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
-    case 8: ln_bwd_kernel<8><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
-    case 1: ln_bwd_kernel<1><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
-    case 2: ln_bwd_kernel<2><<<(int)blocks, 256, smem, st>>>(*a, rm, rows); break;
+    case 4: DAVF_CUDA(launch_pdl(ln_bwd_kernel<4>, dim3((int)blocks), dim3(256), smem, st, *a, rm, rows)); break;
+    case 6: DAVF_CUDA(launch_pdl(ln_bwd_kernel<6>, dim3((int)blocks), dim3(256), smem, st, *a, rm, rows)); break;
+    case 8: DAVF_CUDA(launch_pdl(ln_bwd_kernel<8>, dim3((int)blocks), dim3(256), smem, st, *a, rm, rows)); break;
+    case 1: DAVF_CUDA(launch_pdl(ln_bwd_kernel<1>, dim3((int)blocks), dim3(256), smem, st, *a, rm, rows)); break;
+    case 2: DAVF_CUDA(launch_pdl(ln_bwd_kernel<2>, dim3((int)blocks), dim3(256), smem, st, *a, rm, rows)); break;
     default:
       set_error("layernorm_bwd: D=%d not instantiated", a->D);
       return DAVF_EUNSUPPORTED;

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
                                                          const float* __restrict__ gscale, float inv_count,
                                                          uint16_t* __restrict__ dpred, PatchGeom g, int pred_G, int pred_off,
                                                          int norm_pix) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t patch = (int64_t)blockIdx.x * 8 + warp;
@@ -102,7 +104,7 @@ extern "C" int davf_masked_mse_fwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(geom(g, B, C, H, W, p) == 0, "masked_mse_fwd: unsupported geometry C=%d H=%d W=%d p=%d", C, H, W, p);
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  masked_mse_kernel<false><<<(int)((np + 7) / 8), 256, 0, as_stream(s)>>>(img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix);
+  DAVF_CUDA(launch_pdl(masked_mse_kernel<false>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -115,7 +117,7 @@ extern "C" int davf_masked_mse_bwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(gscale && dpred, "masked_mse_bwd: null pointer");
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  masked_mse_kernel<true><<<(int)((np + 7) / 8), 256, 0, as_stream(s)>>>(img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix);
+  DAVF_CUDA(launch_pdl(masked_mse_kernel<true>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

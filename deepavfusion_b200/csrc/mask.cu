@@ -8,6 +8,8 @@ namespace davf {
 __global__ void mask_rank_kernel(const float* __restrict__ noise, int L, int len_keep,
                                  int64_t* __restrict__ ids_restore, int64_t* __restrict__ ids_keep,
                                  float* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float row[];
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] = noise[(int64_t)b * L + i];
@@ -32,7 +34,7 @@ extern "C" int davf_mask_rank(const float* noise, int B, int L, int len_keep, in
   DAVF_CHECK_ARG(L <= 8192, "mask_rank: L=%d too large for one CTA", L);
   if (B == 0) return DAVF_OK;
   int threads = L < 256 ? ((L + 31) / 32) * 32 : 256;
-  davf::mask_rank_kernel<<<B, threads, L * sizeof(float), davf::as_stream(s)>>>(noise, L, len_keep, ids_restore, ids_keep, mask);
+  DAVF_CUDA(davf::launch_pdl(davf::mask_rank_kernel, dim3(B), dim3(threads), L * sizeof(float), davf::as_stream(s), noise, L, len_keep, ids_restore, ids_keep, mask));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

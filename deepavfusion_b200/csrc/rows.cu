@@ -18,6 +18,8 @@ static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
 // ---------------------------------------------------------------------------------------------
 __global__ void patch_rows_kernel(const float* __restrict__ img, const int64_t* __restrict__ ids_keep,
                                   uint16_t* __restrict__ out, int B, int C, int H, int W, int p, int nK) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gW = W / p;
   const int qpr = p / 4;                         // float4 quads per patch row
   const int64_t quads_per_row = (int64_t)C * p * qpr;
@@ -44,6 +46,8 @@ __global__ void patch_rows_kernel(const float* __restrict__ img, const int64_t* 
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t M, int D,
                                  int g, int G, int off) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = D / 4;
   const int64_t total = M * vpr;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -58,7 +62,30 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, uint16_t* __rest
   }
 }
 
+// out = a + b (+ c), f32, plus a bf16 copy: the gradient fan-in of a tensor with two or three consumers
+// (deepavfusion.py:104-106: x_image / x_audio feed their block and the fusion block, x_fusion feeds all three)
+__global__ void sum_cast_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
+                                float4* __restrict__ out, uint2* __restrict__ out_lp, int64_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = a[i];
+    const float4 w = b[i];
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    if (c) { const float4 u = c[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+    out[i] = v;
+    if (out_lp) {
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      out_lp[i] = o;
+    }
+  }
+}
+
 __global__ void cast_flat_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
     uint2 o;
@@ -74,6 +101,8 @@ __global__ void cast_flat_kernel(const float* __restrict__ src, uint16_t* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void colsum_bf16_kernel(const uint16_t* __restrict__ x, int64_t M, int N, int64_t ld, float* __restrict__ out,
                                    int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float2 red[8][32];
   const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int n = (blockIdx.x * 32 + cp) * 2;
@@ -104,6 +133,8 @@ __global__ void colsum_bf16_kernel(const uint16_t* __restrict__ x, int64_t M, in
 // out[r*D + d] (+)= sum_b x[(b*G + off + r)*D + d]
 __global__ void batchsum_f32_kernel(const float* __restrict__ x, int B, int G, int off, int g, int D,
                                     float* __restrict__ out, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = D / 4;
   const int64_t total = (int64_t)g * vpr;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -124,6 +155,8 @@ __global__ void dec_assemble_fwd_kernel(const float* __restrict__ e, const float
                                         const float* __restrict__ mask_token, const float* __restrict__ pos,
                                         const int64_t* __restrict__ ids_restore, float* __restrict__ seq,
                                         int B, int nK, int nF, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = D / 4;
   const int S = nF + L;
   const int64_t total = (int64_t)B * S * vpr;
@@ -150,6 +183,8 @@ __global__ void dec_assemble_fwd_kernel(const float* __restrict__ e, const float
 __global__ void dec_assemble_bwd_rows_kernel(const float* __restrict__ dseq, const int64_t* __restrict__ ids_keep,
                                              uint16_t* __restrict__ de, uint16_t* __restrict__ def_,
                                              int B, int nK, int nF, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = D / 4;
   const int S = nF + L;
   const int R = nK + nF;
@@ -179,6 +214,8 @@ __global__ void dec_assemble_bwd_rows_kernel(const float* __restrict__ dseq, con
 __global__ void dec_assemble_bwd_reduce_kernel(const float* __restrict__ dseq, const int64_t* __restrict__ ids_restore,
                                                float* __restrict__ dmask_token, float* __restrict__ dpos,
                                                int B, int nK, int nF, int L, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int l = blockIdx.x;
   const int S = nF + L;
   for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
@@ -203,13 +240,24 @@ __global__ void dec_assemble_bwd_reduce_kernel(const float* __restrict__ dseq, c
 
 using namespace davf;
 
+extern "C" int davf_sum_cast(const float* a, const float* b, const float* c, float* out, davf_bf16* out_bf16, int64_t n, davf_stream_t s) {
+  DAVF_CHECK_ARG(a && b && out && n % 4 == 0, "sum_cast: null pointer or n=%lld not a multiple of 4", (long long)n);
+  DAVF_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)out) & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "sum_cast: misaligned pointer");
+  if (n == 0) return DAVF_OK;
+  DAVF_CUDA(launch_pdl(sum_cast_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, as_stream(s), reinterpret_cast<const float4*>(a),
+                       reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(c), reinterpret_cast<float4*>(out),
+                       reinterpret_cast<uint2*>(out_bf16), n / 4));
+  DAVF_LAUNCH_OK();
+  return DAVF_OK;
+}
+
 extern "C" int davf_patch_rows(const float* img, const int64_t* ids_keep, davf_bf16* out, int B, int C, int H, int W,
                                int p, int nK, davf_stream_t s) {
   DAVF_CHECK_ARG(p > 0 && p % 4 == 0 && H % p == 0 && W % p == 0 && W % 4 == 0, "patch_rows: p=%d H=%d W=%d unsupported", p, H, W);
   DAVF_CHECK_ARG(nK > 0 && nK <= (H / p) * (W / p), "patch_rows: nK=%d", nK);
   if (B == 0) return DAVF_OK;
   const int64_t total = (int64_t)B * nK * C * p * (p / 4);
-  patch_rows_kernel<<<grid_for(total, 256), 256, 0, as_stream(s)>>>(img, ids_keep, out, B, C, H, W, p, nK);
+  DAVF_CUDA(launch_pdl(patch_rows_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(s), img, ids_keep, out, B, C, H, W, p, nK));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -217,7 +265,7 @@ extern "C" int davf_patch_rows(const float* img, const int64_t* ids_keep, davf_b
 extern "C" int davf_cast_rows_bf16(const float* src, davf_bf16* dst, int64_t M, int D, int g, int G, int off, davf_stream_t s) {
   DAVF_CHECK_ARG(D % 4 == 0 && g > 0 && G >= g && off >= 0 && off + g <= G, "cast_rows: D=%d g=%d G=%d off=%d", D, g, G, off);
   if (M == 0) return DAVF_OK;
-  cast_rows_kernel<<<grid_for(M * (D / 4), 256), 256, 0, as_stream(s)>>>(src, dst, M, D, g, G, off);
+  DAVF_CUDA(launch_pdl(cast_rows_kernel, dim3(grid_for(M * (D / 4), 256)), dim3(256), 0, as_stream(s), src, dst, M, D, g, G, off));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -225,7 +273,7 @@ extern "C" int davf_cast_rows_bf16(const float* src, davf_bf16* dst, int64_t M, 
 extern "C" int davf_cast_flat_bf16(const float* src, davf_bf16* dst, int64_t n, davf_stream_t s) {
   DAVF_CHECK_ARG(n % 4 == 0, "cast_flat: n=%lld must be a multiple of 4", (long long)n);
   if (n == 0) return DAVF_OK;
-  cast_flat_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(s)>>>(src, dst, n / 4);
+  DAVF_CUDA(launch_pdl(cast_flat_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, as_stream(s), src, dst, n / 4));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -239,14 +287,14 @@ extern "C" int davf_colsum_bf16(const davf_bf16* x, int64_t M, int N, int64_t ld
   if (rpb < 64) rpb = 64;
   rpb = (rpb + 7) / 8 * 8;
   const int gy = (int)((M + rpb - 1) / rpb);
-  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, as_stream(s)>>>(x, M, N, ld, out, (int)rpb);
+  DAVF_CUDA(launch_pdl(colsum_bf16_kernel, dim3(dim3(gx, gy)), dim3(256), 0, as_stream(s), x, M, N, ld, out, (int)rpb));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
 
 extern "C" int davf_batchsum_f32(const float* x, int B, int G, int off, int g, int D, float* out, int accumulate, davf_stream_t s) {
   DAVF_CHECK_ARG(D % 4 == 0 && g > 0 && off >= 0 && off + g <= G, "batchsum: D=%d g=%d G=%d off=%d", D, g, G, off);
-  batchsum_f32_kernel<<<grid_for((int64_t)g * (D / 4), 128), 128, 0, as_stream(s)>>>(x, B, G, off, g, D, out, accumulate);
+  DAVF_CUDA(launch_pdl(batchsum_f32_kernel, dim3(grid_for((int64_t)g * (D / 4), 128)), dim3(128), 0, as_stream(s), x, B, G, off, g, D, out, accumulate));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -256,8 +304,8 @@ extern "C" int davf_decoder_assemble_fwd(const float* e, const float* ef, const 
                                          davf_stream_t s) {
   DAVF_CHECK_ARG(D % 4 == 0 && nK <= L && nF >= 0, "decoder_assemble_fwd: D=%d nK=%d L=%d", D, nK, L);
   if (B == 0) return DAVF_OK;
-  dec_assemble_fwd_kernel<<<grid_for((int64_t)B * (nF + L) * (D / 4), 256), 256, 0, as_stream(s)>>>(
-      e, ef, mask_token, pos, ids_restore, seq, B, nK, nF, L, D);
+  DAVF_CUDA(launch_pdl(dec_assemble_fwd_kernel, dim3(grid_for((int64_t)B * (nF + L) * (D / 4), 256)), dim3(256), 0, as_stream(s), 
+      e, ef, mask_token, pos, ids_restore, seq, B, nK, nF, L, D));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -267,10 +315,10 @@ extern "C" int davf_decoder_assemble_bwd(const float* dseq, const int64_t* ids_k
                                          int B, int nK, int nF, int L, int D, davf_stream_t s) {
   DAVF_CHECK_ARG(D % 4 == 0 && nK <= L, "decoder_assemble_bwd: D=%d nK=%d L=%d", D, nK, L);
   if (B == 0) return DAVF_OK;
-  dec_assemble_bwd_rows_kernel<<<grid_for((int64_t)B * (nK + nF) * (D / 4), 256), 256, 0, as_stream(s)>>>(
-      dseq, ids_keep, de, def_, B, nK, nF, L, D);
+  DAVF_CUDA(launch_pdl(dec_assemble_bwd_rows_kernel, dim3(grid_for((int64_t)B * (nK + nF) * (D / 4), 256)), dim3(256), 0, as_stream(s), 
+      dseq, ids_keep, de, def_, B, nK, nF, L, D));
   DAVF_LAUNCH_OK();
-  dec_assemble_bwd_reduce_kernel<<<L, 128, 0, as_stream(s)>>>(dseq, ids_restore, dmask_token, dpos, B, nK, nF, L, D);
+  DAVF_CUDA(launch_pdl(dec_assemble_bwd_reduce_kernel, dim3(L), dim3(128), 0, as_stream(s), dseq, ids_restore, dmask_token, dpos, B, nK, nF, L, D));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }

@@ -74,6 +74,37 @@ def linear_bwd(st: ParamStore, dy: Tensor, x: Tensor, W: nn.Parameter, b: Option
     return K.gemm(dy, _w2d(st.lowp(W), cols), True, False, **epi)
 
 
+class _Branches:
+    """Independent launches of one region on auxiliary streams.  ``run(i, fn)`` forks stream i off the region's stream,
+    calls ``fn`` there and marks the tensors it returns as used by the region's stream; ``join()`` makes the region's
+    stream wait for every branch that ran.  Without auxiliary streams (CPU tensors, DAVF_STREAMS=0) everything runs inline."""
+
+    def __init__(self, st: ParamStore):
+        self.aux = st.aux_streams(2)
+        self.cur = torch.cuda.current_stream() if self.aux else None
+        self.used = set()
+
+    def run(self, i: int, fn):
+        if not self.aux:
+            return fn()
+        s = self.aux[i % len(self.aux)]
+        if i % len(self.aux) not in self.used:
+            s.wait_stream(self.cur)
+            self.used.add(i % len(self.aux))
+        with torch.cuda.stream(s):
+            out = fn()
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.cur)
+        return out
+
+    def join(self):
+        if self.aux:
+            for i in self.used:
+                self.cur.wait_stream(self.aux[i])
+            self.used = set()
+
+
 def _f32_rows(t: Tensor) -> Tensor:
     return t.reshape(-1, t.shape[-1])
 
@@ -175,6 +206,31 @@ class BroadcastTokensFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# a5  a tensor with several consumers (deepavfusion.py:104-106): backward = ONE fan-in kernel
+# --------------------------------------------------------------------------------------------
+class FanOutFn(torch.autograd.Function):
+    """``x`` feeds ``n`` consumers (x_image / x_audio: their own block and the fusion block; x_fusion: all three blocks).
+    Forward returns ``n`` aliases; backward sums the consumers' gradients in one kernel that also writes the bf16 copy
+    the upstream region needs as a GEMM operand -- instead of autograd's n - 1 add kernels plus a cast."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, n: int, st: ParamStore):
+        ctx.st = st
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        parts = [g.contiguous() for g in grads if g is not None]
+        if not parts:
+            return None, None, None
+        if len(parts) == 1:
+            return parts[0], None, None
+        out, lp = K.sum_cast(parts)
+        ctx.st.stash_lowp_grad(out, lp)
+        return out, None, None
+
+
+# --------------------------------------------------------------------------------------------
 # a3  attention half of a timm Block:  y = x + proj(attn(qkv(LN(cat(xp, x)))))  on the live rows
 # --------------------------------------------------------------------------------------------
 class AttnBranchFn(torch.autograd.Function):
@@ -224,11 +280,9 @@ class AttnBranchFn(torch.autograd.Function):
         do = linear_bwd(st, dyb, o.view(B * n, D), m.proj_w, m.proj_b, defer=wg)      # [B*n, D] bf16
         dqkv = torch.empty_like(qkv)
         d5 = dqkv.view(B, S, 3, H, hd)
-        if nP:
-            d5[:, :nP, 0].zero_()                                                     # dead queries
         q5 = qkv.view(B, S, 3, H, hd)
         K.attention_bwd(q5[:, nP:, 0], q5[:, :, 1], q5[:, :, 2], do.view(B, n, H, hd), lse, hd ** -0.5,
-                        d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2], o=o)
+                        d5[:, nP:, 0], d5[:, :, 1], d5[:, :, 2], o=o, dq_dead_rows=nP)      # (also zero-fills the dead query slots)
         dxn = linear_bwd(st, dqkv, xn, m.qkv_w, m.qkv_b, defer=wg)                    # [B*S, D] bf16
         launch_wgrads(st, wg)
         gw, gb = st.grad(m.norm_w), st.grad(m.norm_b)
@@ -413,10 +467,12 @@ class FusionAttnFn(torch.autograd.Function):
         scale = hd ** -0.5                                                          # fusion_blocks.py:220-222
         L = FusionAttnFn._lins(m)
         seg = [0, nmm, nmm + nv, F]
+        br = _Branches(m.store)           # independent small launches of the block run as parallel branches
+        xv_n, _, mean_v, rstd_v = br.run(0, lambda: K.layernorm_fwd(xv, None, m.n_img_w.data, m.n_img_b.data, m.eps))
+        xa_n, _, mean_a, rstd_a = br.run(1, lambda: K.layernorm_fwd(xa, None, m.n_aud_w.data, m.n_aud_b.data, m.eps))
         mm_b, mm_f, mean_m, rstd_m = K.layernorm_fwd(xmm, None, m.n_mm_w.data, m.n_mm_b.data, m.eps, True, True, seg)
         m2, mv, ma = mm_b[:B * nmm], mm_b[B * nmm:B * (nmm + nv)], mm_b[B * (nmm + nv):]
-        xv_n, _, mean_v, rstd_v = K.layernorm_fwd(xv, None, m.n_img_w.data, m.n_img_b.data, m.eps)
-        xa_n, _, mean_a, rstd_a = K.layernorm_fwd(xa, None, m.n_aud_w.data, m.n_aud_b.data, m.eps)
+        br.join()
         out = torch.empty(B * F, D, dtype=torch.float32, device=xmm.device)
         res = mm_f if drop is None else None        # DropPath: the three projections land in `out` alone, the residual is added scaled
         Nv, Na = xv_n.shape[0] // B, xa_n.shape[0] // B
@@ -424,8 +480,9 @@ class FusionAttnFn(torch.autograd.Function):
         # every Linear that only needs the normed inputs: CrossAttention q / kv of both modalities (:46-52) + pair q (:252)
         qv, kvv, qa, kva, q2 = group_fwd([(mv, L.q_v, {}), (xv_n, L.kv_v, {}), (ma, L.q_a, {}), (xa_n, L.kv_a, {}), (m2, L.q2, {})])
         kvv5, kva5 = kvv.view(B, Nv, 2, H, hd), kva.view(B, Na, 2, H, hd)
+        oa, lse_a = br.run(0, lambda: K.attention_fwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], scale))
         ov, lse_v = K.attention_fwd(qv.view(B, nv, H, hd), kvv5[:, :, 0], kvv5[:, :, 1], scale)
-        oa, lse_a = K.attention_fwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], scale)
+        br.join()
         # out[b, off:off+n] = LN_mm(xmm)[b, off:...] + proj(.) ; the bf16 proj outputs feed the pair attention
         (_, pv), (_, pa) = group_fwd([
             (ov.view(B * nv, D), L.proj_v, dict(want_aux=True, res=res, out=out, window=(nv, F, nmm))),
@@ -435,8 +492,11 @@ class FusionAttnFn(torch.autograd.Function):
         q2v = q2.view(B, nmm, H, dq)
         k_v, v_v = kv2v.view(B, nv, qk + D)[:, :, :qk].unflatten(2, (H, dq)), kv2v.view(B, nv, qk + D)[:, :, qk:].unflatten(2, (H, hd))
         k_a, v_a = kv2a.view(B, na, qk + D)[:, :, :qk].unflatten(2, (H, dq)), kv2a.view(B, na, qk + D)[:, :, qk:].unflatten(2, (H, hd))
-        o2, lse2v = K.attention_fwd(q2v, k_v, v_v, scale)
-        _, lse2a = K.attention_fwd(q2v, k_a, v_a, scale, out=o2, accumulate=True)
+        # the two halves add into one zero-initialised buffer with bf16x2 atomics, so they need no order
+        o2 = torch.zeros(B, nmm, H, hd, dtype=torch.bfloat16, device=xmm.device)
+        _, lse2a = br.run(0, lambda: K.attention_fwd(q2v, k_a, v_a, scale, out=o2, accumulate=2))
+        _, lse2v = K.attention_fwd(q2v, k_v, v_v, scale, out=o2, accumulate=2)
+        br.join()
         o2 = o2.view(B * nmm, D)
         K.gemm(o2, L.proj.w, bias=L.proj.b, res=res, out=out, window=(nmm, F, 0))
         if drop is not None:                         # xmm + drop_path(res_fusion), fusion_blocks.py:283
@@ -475,7 +535,8 @@ class FusionAttnFn(torch.autograd.Function):
         wg = []                                      # the block's ten wgrads leave in two grouped launches at the end
         (do2,) = group_bwd(st, [(dr2, o2, L.proj, {})], wg)
         do2 = do2.view(B, nmm, H, hd)
-        dq2 = torch.empty_like(q2)
+        br = _Branches(st)
+        dq2 = torch.zeros_like(q2)                   # both halves of the pair attention add into it (bf16x2 atomics)
         dkv2v, dkv2a = torch.empty_like(kv2v), torch.empty_like(kv2a)
 
         def split(t, n):
@@ -484,8 +545,9 @@ class FusionAttnFn(torch.autograd.Function):
         q2v = q2.view(B, nmm, H, dq)
         (k_v, v_v), (k_a, v_a) = split(kv2v, nv), split(kv2a, na)
         (dk_v, dv_v), (dk_a, dv_a) = split(dkv2v, nv), split(dkv2a, na)
-        K.attention_bwd(q2v, k_v, v_v, do2, lse2v, scale, dq2.view(B, nmm, H, dq), dk_v, dv_v)
-        K.attention_bwd(q2v, k_a, v_a, do2, lse2a, scale, dq2.view(B, nmm, H, dq), dk_a, dv_a, accumulate_dq=True)
+        br.run(0, lambda: K.attention_bwd(q2v, k_a, v_a, do2, lse2a, scale, dq2.view(B, nmm, H, dq), dk_a, dv_a, accumulate_dq=2))
+        K.attention_bwd(q2v, k_v, v_v, do2, lse2v, scale, dq2.view(B, nmm, H, dq), dk_v, dv_v, accumulate_dq=2)
+        br.join()
         # d proj-output of each aggregation group = residual path (rows of dout) + [dk | dv] through the stacked weight
         idx_v = FusionAttnFn._idx(m, B, F, nmm, nv, dout.device)
         idx_a = FusionAttnFn._idx(m, B, F, nmm + nv, na, dout.device)
@@ -498,21 +560,22 @@ class FusionAttnFn(torch.autograd.Function):
         dqv, dkvv, dqa, dkva = torch.empty_like(qv), torch.empty_like(kvv), torch.empty_like(qa), torch.empty_like(kva)
         kvv5, dkvv5 = kvv.view(B, Nv, 2, H, hd), dkvv.view(B, Nv, 2, H, hd)
         kva5, dkva5 = kva.view(B, Na, 2, H, hd), dkva.view(B, Na, 2, H, hd)
+        br.run(0, lambda: K.attention_bwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], do_a.view(B, na, H, hd), lse_a, scale,
+                                          dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1], o=oa.view(B, na, H, hd)))
         K.attention_bwd(qv.view(B, nv, H, hd), kvv5[:, :, 0], kvv5[:, :, 1], do_v.view(B, nv, H, hd), lse_v, scale,
                         dqv.view(B, nv, H, hd), dkvv5[:, :, 0], dkvv5[:, :, 1], o=ov.view(B, nv, H, hd))
-        K.attention_bwd(qa.view(B, na, H, hd), kva5[:, :, 0], kva5[:, :, 1], do_a.view(B, na, H, hd), lse_a, scale,
-                        dqa.view(B, na, H, hd), dkva5[:, :, 0], dkva5[:, :, 1], o=oa.view(B, na, H, hd))
+        br.join()
         _, _, dxv_n, dxa_n = group_bwd(st, [(dqv, mv, L.q_v, dict(out=dmv)), (dqa, ma, L.q_a, dict(out=dma)),
                                             (dkvv, xv_n, L.kv_v, {}), (dkva, xa_n, L.kv_a, {})], wg)
         launch_wgrads(st, wg)
 
-        dxv, _ = K.layernorm_bwd(xv, None, m.n_img_w.data, mean_v, rstd_v, dxv_n, None, None, None,
-                                 st.grad(m.n_img_w), st.grad(m.n_img_b))
-        dxa, _ = K.layernorm_bwd(xa, None, m.n_aud_w.data, mean_a, rstd_a, dxa_n, None, None, None,
-                                 st.grad(m.n_aud_w), st.grad(m.n_aud_b))
+        gw_v, gb_v, gw_a, gb_a = st.grad(m.n_img_w), st.grad(m.n_img_b), st.grad(m.n_aud_w), st.grad(m.n_aud_b)
+        dxv, _ = br.run(0, lambda: K.layernorm_bwd(xv, None, m.n_img_w.data, mean_v, rstd_v, dxv_n, None, None, None, gw_v, gb_v))
+        dxa, _ = br.run(1, lambda: K.layernorm_bwd(xa, None, m.n_aud_w.data, mean_a, rstd_a, dxa_n, None, None, None, gw_a, gb_a))
         seg = [0, nmm, nmm + nv, F]
         dxmm, _ = K.layernorm_bwd(xmm, None, m.n_mm_w.data, mean_m, rstd_m, dseg, d_res, None, None,
                                   st.grad(m.n_mm_w), st.grad(m.n_mm_b), seg_start=seg)
+        br.join()
         _done(m)
         return dxmm, dxv, dxa, None, None, None
 

@@ -83,6 +83,20 @@ def cast_flat_bf16(src: Tensor, dst: Tensor) -> None:
     check(_cabi.lib().davf_cast_flat_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "davf_cast_flat_bf16")
 
 
+def sum_cast(parts: Sequence[Tensor], want_bf16: bool = True):
+    """f32 sum of two or three equally shaped tensors, plus its bf16 copy: (sum, bf16 or None)."""
+    assert 2 <= len(parts) <= 3
+    a = _need(parts[0], torch.float32, "parts[0]")
+    for t in parts[1:]:
+        _need(t, torch.float32, "parts[i]")
+        assert t.shape == a.shape
+    out = torch.empty_like(a)
+    lp = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    check(_cabi.lib().davf_sum_cast(_ptr(a), _ptr(parts[1]), _ptr(parts[2] if len(parts) > 2 else None), _ptr(out), _ptr(lp), a.numel(), _stream()),
+          "davf_sum_cast")
+    return out, lp
+
+
 def colsum_bf16(x: Tensor, out: Tensor) -> None:
     """out[n] += sum_m x[m, n]   (x bf16 [M,N] row-major view with stride(1) == 1)."""
     _need(x, torch.bfloat16, "x", contiguous=False); _need(out, torch.float32, "out")
@@ -323,9 +337,11 @@ def attention_fwd(q: Tensor, k: Tensor, v: Tensor, scale: float, out: Optional[T
 
 
 def attention_bwd(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, lse: Tensor, scale: float,
-                  dq: Tensor, dk: Tensor, dv: Tensor, accumulate_dq: bool = False, o: Optional[Tensor] = None) -> None:
+                  dq: Tensor, dk: Tensor, dv: Tensor, accumulate_dq: bool = False, o: Optional[Tensor] = None,
+                  dq_dead_rows: int = 0) -> None:
     """Writes dq / dk / dv (strided bf16 views shaped like q / k / v).  ``o`` (forward output) is optional:
-    with it the kernel uses the one-pass D_i = dO_i . O_i form."""
+    with it the kernel uses the one-pass D_i = dO_i . O_i form.  ``dq_dead_rows``: that many rows in front of dq's
+    first row (the dead fusion-prefix query slots of a packed dqkv buffer) are zero-filled by the same launch."""
     B, Nq, H, dqk = q.shape
     Nk, dvd = k.shape[1], v.shape[3]
     a = _cabi.AttnBwdArgs()
@@ -339,6 +355,7 @@ def attention_bwd(q: Tensor, k: Tensor, v: Tensor, d_o: Tensor, lse: Tensor, sca
     a.dv_, a.dv_bs, a.dv_rs = _bhs(dv, "dv")
     a.B, a.H, a.Nq, a.Nk, a.dqk, a.dv = B, H, Nq, Nk, dqk, dvd
     a.scale, a.accumulate_dq = float(scale), int(accumulate_dq)
+    a.dq_dead_rows = int(dq_dead_rows)
     if o is not None:
         a.o, a.o_bs, a.o_rs = _bhs(o, "o")
         assert a.o % 16 == 0 and a.o_bs % 8 == 0 and a.o_rs % 8 == 0, "o rows must be 16-byte aligned"
@@ -525,6 +542,11 @@ KIND_GEMM_2CTA, KIND_ATTN_TC, KIND_ATTN_MMA = 1, 2, 3
 def launch_count_kind(kind: int) -> int:
     """Launches of one kernel family so far (see davf_launch_count_kind)."""
     return int(_cabi.lib().davf_launch_count_kind(int(kind)))
+
+
+def set_pdl(on: bool) -> None:
+    """Programmatic dependent launch on / off (see davf_set_pdl)."""
+    check(_cabi.lib().davf_set_pdl(int(on)), "davf_set_pdl")
 
 
 def set_gemm_impl(impl: int) -> None:

@@ -154,12 +154,19 @@ class DeepAVFusion(nn.Module):
                     x_audio = blk_audio(x_audio)
             else:
                 # deepavfusion.py:104-107: the modality blocks see the fusion tokens as extra keys / values;
-                # the fusion block reads the PRE-block modality tokens.
-                _x_image = blk_image(x_image, prefix=x_fusion)
+                # the fusion block reads the PRE-block modality tokens.  Each input has two / three consumers: FanOutFn
+                # makes the gradient fan-in one kernel, run on the stream of the branch that consumes the sum.
+                store = self.__dict__["_davf_store"]
+                xi_blk, xi_fus = Fn.FanOutFn.apply(x_image, 2, store)
                 with on(side[0] if side else None):
-                    _x_audio = blk_audio(x_audio, prefix=x_fusion)
+                    xa_blk, xa_fus = Fn.FanOutFn.apply(x_audio, 2, store)
                 with on(side[1] if side else None):
-                    x_fusion = blk_fusion(x_fusion, x_image, x_audio)
+                    xf_img, xf_aud, xf_fus = Fn.FanOutFn.apply(x_fusion, 3, store)
+                _x_image = blk_image(xi_blk, prefix=xf_img)
+                with on(side[0] if side else None):
+                    _x_audio = blk_audio(xa_blk, prefix=xf_aud)
+                with on(side[1] if side else None):
+                    x_fusion = blk_fusion(xf_fus, xi_fus, xa_fus)
                 x_image, x_audio = _x_image, _x_audio
             join()
             if side:      # next layer (and the final norms on `cur`) read these across streams

@@ -273,6 +273,22 @@ class ParamStore:
             self.__dict__["_wgrad_stream"] = ws
         return ws
 
+    def aux_streams(self, n: int = 2):
+        """``n`` auxiliary streams for independent small launches INSIDE one backward / forward region (the fusion block's
+        three LayerNorms, its two cross attentions, the two halves of the pair attention): forked from and joined back
+        into the region's own stream, so in the captured step graph they are parallel branches and the region's
+        dependent chain -- the critical path of every encoder layer -- gets shorter.  None on CPU tensors or with
+        DAVF_STREAMS=0 / DAVF_AUX_STREAMS=0."""
+        aux = self.__dict__.get("_aux_streams", False)
+        if aux is False:
+            import os
+            aux = None
+            if self.flat_g.is_cuda and os.environ.get("DAVF_STREAMS", "1") != "0" and os.environ.get("DAVF_AUX_STREAMS", "1") != "0":
+                aux = [torch.cuda.Stream(self.flat_g.device) for _ in range(n)]
+                self.side_streams.extend(aux)
+            self.__dict__["_aux_streams"] = aux
+        return aux
+
     def join_side_streams(self, stream=None) -> None:
         """Make ``stream`` (default: the stream the last forward was issued on) wait for the side streams.
         The engine callback may run on an autograd worker thread whose *current* stream is not the caller's,

@@ -53,6 +53,11 @@ int64_t davf_launch_count(void);
 /* The same, by kernel family: 1 = CTA-pair (cta_group::2) tcgen05 GEMM, 2 = tcgen05/TMEM attention, 3 = mma.sync attention
  * (small-query cases); any other value = all.  Lets tests and benches prove which kernel variant served a call. */
 int64_t davf_launch_count_kind(int kind);
+/* 1 (env DAVF_PDL=1; default 0): kernels are launched with programmatic stream serialization -- each kernel's set-up
+ * (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of its predecessor on the stream; memory ordering
+ * is unchanged (griddepcontrol.wait precedes the first global access of every kernel).  Off by default: with the step's
+ * concurrent streams it measured 2 % slower on B200 (early-resident dependents hold SMs the other streams could use). */
+int davf_set_pdl(int on);
 
 /* ---- K2: MAE random masking ----------------------------------------------------------------
  * Replaces avmae.py:127-140 (rand -> argsort -> argsort -> slice -> gather) given the noise.
@@ -73,6 +78,11 @@ int davf_patch_rows(const float* img, const int64_t* ids_keep, davf_bf16* out,
  * the source, off = first row); pass g = G = M, off = 0 for a plain cast. */
 int davf_cast_rows_bf16(const float* src, davf_bf16* dst, int64_t M, int D, int g, int G, int off,
                         davf_stream_t s);
+
+/* Gradient fan-in: out = a + b (+ c when non-NULL), f32 [n], and (when out_bf16 is non-NULL) its bf16 copy.  Replaces the
+ * autograd accumulation of the gradients of a tensor with several consumers (deepavfusion.py:104-106: x_image / x_audio feed
+ * their own block and the fusion block, x_fusion feeds all three) together with the cast that made the GEMM operand. */
+int davf_sum_cast(const float* a, const float* b, const float* c, float* out, davf_bf16* out_bf16, int64_t n, davf_stream_t s);
 
 /* Column sums (bias gradients; replaces autograd's sum-to-size for every Linear bias):
  * out[n] += sum_m x[m*ld + n], x bf16 [M,N], out f32 [N] (atomic accumulate). */
@@ -185,7 +195,9 @@ int davf_gemm_grouped(const davf_gemm_args* a, int count, davf_stream_t s);
  * o rows  o + b*o_bs + i*o_rs + h*dv.   All bf16; strides in elements, so packed qkv buffers and
  * query sub-ranges (live rows only) need no copies.
  * lse f32 [B,H,Nq] = log-sum-exp of the scaled logits (saved for backward).
- * accumulate != 0: o += result (used to add the two factorised pair attentions).
+ * accumulate != 0: o += result (used to add the two factorised pair attentions): 1 = read-modify-write
+ * (launches adding into one buffer must be ordered by the caller), 2 = bf16x2 atomic adds into a zero-initialised buffer
+ * (such launches may run concurrently on different streams).
  * Supported (dqk, dv): (64,64), (32,32), (16,64).  Nk <= 256.  q / k / v rows must be 16-byte aligned
  * (strides multiples of 8 elements). */
 typedef struct {
@@ -200,7 +212,7 @@ typedef struct {
 int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s);
 
 /* Backward: given dO (layout of o) writes dq / dk / dv with the layouts of q / k / v (separate
- * stride sets so gradients can land in a packed dqkv buffer).  accumulate_dq != 0: dq += .
+ * stride sets so gradients can land in a packed dqkv buffer).  accumulate_dq != 0: dq += (1 / 2 as for the forward).
  * The softmax-Jacobian row term D_i is computed from the recomputed probabilities (exact, used for the
  * tiny fusion-token attentions) unless the forward output `o` is supplied (see the struct). */
 typedef struct {
@@ -217,6 +229,10 @@ typedef struct {
   /* optional forward output (layout o_bs / o_rs, heads packed): if given, D_i = dO_i . O_i (one pass, the
    * flash-attention form); if NULL, D_i = sum_j P_ij dP_ij from a first pass over the recomputed scores. */
   const davf_bf16* o; int64_t o_bs; int64_t o_rs;
+  /* dq_dead_rows > 0: the rows [-dq_dead_rows, 0) in front of dq's first row (same strides, every head's dqk columns) are
+   * zero-filled: the query slots of the fusion-token prefix rows, whose block outputs the reference discards
+   * (deepavfusion.py:104-105), inside a packed dqkv buffer that the qkv dgrad GEMM reads in full. */
+  int dq_dead_rows;
 } davf_attn_bwd_args;
 int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s);
 

@@ -54,6 +54,13 @@ def cast_flat_bf16(src, dst):
     dst.copy_(src.to(bf16))
 
 
+def sum_cast(parts, want_bf16=True):
+    out = parts[0] + parts[1]
+    if len(parts) > 2:
+        out = out + parts[2]
+    return out, (out.to(bf16) if want_bf16 else None)
+
+
 def colsum_bf16(x, out):
     out += x.float().sum(0)
 
@@ -192,7 +199,10 @@ def attention_fwd(q, k, v, scale, out=None, accumulate=False):
     return out, lse.contiguous()
 
 
-def attention_bwd(q, k, v, d_o, lse, scale, dq, dk, dv, accumulate_dq=False, o=None):
+def attention_bwd(q, k, v, d_o, lse, scale, dq, dk, dv, accumulate_dq=False, o=None, dq_dead_rows=0):
+    if dq_dead_rows:          # dq is a view [B, n, H, d] of a larger buffer: zero the rows in front of it
+        B_, n_, H_, d_ = dq.shape
+        torch.as_strided(dq, (B_, dq_dead_rows, H_, d_), dq.stride(), dq.storage_offset() - dq_dead_rows * dq.stride(1)).zero_()
     qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3)
     dof = d_o.float().permute(0, 2, 1, 3)
     p = torch.exp(qf @ kf.transpose(-1, -2) * scale - lse[..., None])

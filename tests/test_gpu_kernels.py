@@ -283,7 +283,8 @@ def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
         _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
         tc = K.launch_count_kind(K.KIND_ATTN_TC) - n0
         eligible = impl == 0 and Nq > 16 and dqk == dv and dqk in (32, 64)
-        assert tc == (2 if eligible else 0), tc          # forward + the one-pass backward (the two-pass backward has no forward output)
+        packed = dqk == dv and Nq + skip <= Nk and skip > 0
+        assert tc == ((3 if packed else 2) if eligible else 0), tc    # forward + the one-pass backward(s); the two-pass backward has no forward output
     finally:
         K.set_attn_impl(0)
 
@@ -312,6 +313,15 @@ def _attention_case(K, B, H, Nq, Nk, dqk, dv, skip):
     K.attention_bwd(q, k, v, do, lse, scale, dq2, dk2, dv2, o=o)
     E.attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), lse.cpu(), scale, edq, edk, edv, o=o.cpu())
     close(dq2, edq, 3e-2, 3e-2, "dq (o)"); close(dk2, edk, 3e-2, 3e-2, "dk (o)"); close(dv2, edv, 3e-2, 3e-2, "dv (o)")
+    if dqk == dv and Nq + skip <= Nk and skip > 0:
+        # gradients written into a packed dqkv buffer (as the encoder blocks do); the dead query slots in front of dq are zero-filled
+        dqkv = torch.full_like(qkv, 7.0)
+        K.attention_bwd(q, k, v, do, lse, scale, dqkv[:, skip:skip + Nq, 0], dqkv[:, :, 1], dqkv[:, :, 2], o=o, dq_dead_rows=skip)
+        assert float(dqkv[:, :skip, 0].float().abs().max()) == 0.0
+        if skip + Nq < Nk:
+            assert float((dqkv[:, skip + Nq:, 0].float() - 7.0).abs().max()) == 0.0      # rows behind dq are not touched
+        close(dqkv[:, skip:skip + Nq, 0], edq, 3e-2, 3e-2, "dq (packed)"); close(dqkv[:, :, 1], edk, 3e-2, 3e-2, "dk (packed)")
+        close(dqkv[:, :, 2], edv, 3e-2, 3e-2, "dv (packed)")
 
 
 # ---------------------------------------------------------------- decoder assembly / loss / optimizer
