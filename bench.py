@@ -748,7 +748,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ:
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG_FILE" not in os.environ:
         # record what NCCL picked for the exchange step (algorithm / protocol / channels / NVLS) in its own log files
         d = os.path.join("/tmp", f"davf_nccl_{os.environ.get('MASTER_PORT', '0')}")
         os.makedirs(d, exist_ok=True)

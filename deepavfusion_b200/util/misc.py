@@ -136,3 +136,74 @@ def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
     if norm_type == math.inf:
         return max(p.grad.detach().abs().max() for p in parameters)
     return torch.norm(torch.stack([torch.norm(p.grad.detach(), norm_type) for p in parameters]), norm_type)
+
+
+class CheckpointManager:
+    """Mirror of reference util/misc.py:222-309: same constructor, ``resume()`` / ``checkpoint(epoch, save_dict, is_best)``
+    and the same file layout -- ``checkpoint_latest.pth`` (plus ``checkpoint_best.pth`` / ``checkpoint_{epoch:04d}.pth``)
+    holding ``{name: module.state_dict() or tensor}`` for every entry of ``Trainer.module_dict()`` ('state_dict',
+    'optimizer', 'n_steps', ...) together with 'epoch' and the caller's metrics.  Because the fused optimizer's
+    ``state_dict()`` has ``torch.optim.AdamW``'s shape, files written here resume under the reference and vice versa.
+    Tensors are saved as independent CPU copies (the parameters are views into one flat buffer)."""
+
+    def __init__(self, modules, ckpt_dir, epochs, save_freq=None):
+        import os
+        self.modules, self.ckpt_dir, self.epochs, self.save_freq = modules, ckpt_dir, epochs, save_freq
+        self.world_size, self.rank = dist_utils.get_world_size(), dist_utils.get_rank()
+        if self.rank == 0:
+            os.makedirs(self.ckpt_dir, exist_ok=True)
+
+    @staticmethod
+    def _to_cpu(state):
+        if isinstance(state, dict):
+            return {k: CheckpointManager._to_cpu(v) for k, v in state.items()}
+        if isinstance(state, (list, tuple)):
+            return type(state)(CheckpointManager._to_cpu(v) for v in state)
+        if isinstance(state, torch.Tensor):
+            return state.detach().to("cpu", copy=True).contiguous()
+        return state
+
+    def create_state_dict(self, save_dict=None):
+        state = {}
+        for k, mod in self.modules.items():
+            if mod is None:
+                state[k] = None
+            elif isinstance(mod, torch.Tensor):
+                state[k] = mod.detach().to("cpu", copy=True)
+            else:
+                state[k] = self._to_cpu(mod.state_dict())
+        if save_dict is not None:
+            state.update(save_dict)
+        return state
+
+    def resume(self):
+        import os
+        fname = os.path.join(self.ckpt_dir, "checkpoint_latest.pth")
+        start_epoch, metrics = 0, {}
+        if os.path.isfile(fname):
+            ckpt = torch.load(fname, map_location="cpu", weights_only=False)
+            for k, mod in self.modules.items():
+                if mod is None:
+                    continue
+                if isinstance(mod, torch.Tensor):
+                    mod.data[:] = ckpt[k].data
+                else:
+                    mod.load_state_dict(ckpt[k])
+            start_epoch = ckpt["epoch"]
+            metrics = {k: v for k, v in ckpt.items() if k not in self.modules and k != "epoch"}
+            print(f"=> loaded checkpoint '{fname}' (epoch {start_epoch})")
+        return start_epoch, metrics
+
+    def checkpoint(self, epoch, save_dict=None, is_best=False):
+        import os
+        if self.rank != 0:
+            return
+        state = self.create_state_dict(save_dict)
+        state.setdefault("epoch", epoch)
+        targets = ["checkpoint_latest.pth"]
+        if is_best:
+            targets.append("checkpoint_best.pth")
+        if self.save_freq is not None and (epoch % self.save_freq == 0 or epoch == self.epochs):
+            targets.append(f"checkpoint_{epoch:04d}.pth")
+        for t in targets:
+            torch.save(state, os.path.join(self.ckpt_dir, t))

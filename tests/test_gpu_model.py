@@ -294,3 +294,30 @@ def test_graph_capture_is_side_effect_free_and_accumulates_like_eager():
         assert abs(a - b) <= 2e-3 * abs(a), (ne, ng)
     assert float((pe - pg).norm()) <= 1e-5 * float(pe.norm())
     assert float((me - mg).norm()) <= 2e-3 * float(me.norm()) and float((ve - vg).norm()) <= 2e-3 * float(ve.norm())
+
+
+def test_checkpoint_manager_resume_gpu(tmp_path):
+    """f1 on the CUDA path: CheckpointManager file layout, torch.optim.AdamW-shaped optimizer entry, resume == uninterrupted."""
+    from test_trainer_cpu import _checkpoint_resume_case
+    _checkpoint_resume_case("cuda", tmp_path)
+
+
+def test_return_embs_matches_oracle_layers():
+    """f3 (deepavfusion.py:108-109, knn_probe.py:99): ``return_embs=True`` hands back every layer's (x_image, x_audio,
+    x_fusion); the last entry, final-normed, is the encoder output, and every layer matches the oracle's activations."""
+    cfg = U.tiny_cfg()
+    sd = O.build_state(cfg, seed=0)
+    image, audio = U.make_inputs(cfg, 2)
+    model = U.build_model(cfg, "cuda")
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        xi, xa, xf, embs = model.encoder(image.cuda(), audio.cuda(), return_embs=True)
+        yi, ya, yf = model.encoder(image.cuda(), audio.cuda())
+    assert len(embs) == cfg.depth and all(len(e) == 3 for e in embs)
+    assert torch.equal(xi, yi) and torch.equal(xa, ya) and torch.equal(xf, yf)
+    P = O._Prec(False)
+    ri, ra, rf = O.encoder_forward(P, sd, cfg, image, audio)
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm())
+    assert rel(xi, ri) < 2e-2 and rel(xa, ra) < 2e-2 and rel(xf, rf) < 2e-2
+    for e in embs:
+        assert e[0].shape == xi.shape and e[1].shape == xa.shape and e[2].shape == xf.shape and bool(torch.isfinite(e[2]).all())

@@ -229,3 +229,67 @@ def test_data_parallel_gloo_world2(tmp_path, monkeypatch):
     # not 1e-6: the emulated GEMMs (MKL f32) are not bit-identical per row for different batch sizes, and a
     # 1-ulp f32 difference occasionally flips a bf16 rounding; the same split in ONE process gives 1.4e-3.
     assert rel < 5e-3, rel
+
+
+def _checkpoint_resume_case(device, tmp_path):
+    """a run checkpointed through CheckpointManager (reference layout, misc.py:222-309) and resumed into
+    fresh objects continues exactly like the uninterrupted run; the 'optimizer' entry loads into a stock
+    ``torch.optim.AdamW`` (reference train.py:93) and a state written by the stock optimizer loads back."""
+    from deepavfusion_b200.util.misc import CheckpointManager, Trainer
+    cfg = U.tiny_cfg()
+    image, audio = (t.to(device) for t in U.make_inputs(cfg, 2))
+    noises = [n.to(device) for n in U.make_noise(cfg, 2)]
+    sd = O.build_state(cfg, seed=0)
+
+    def fresh():
+        model = U.build_model(cfg, device); model.load_state_dict(sd)
+        opt = torch.optim.AdamW(_groups(model), lr=1e-3, betas=(0.9, 0.95))
+        return Trainer(model, optimizer=opt)
+
+    def run(trainer, steps):
+        for _ in range(steps):
+            with U.inject_rand([n.clone() for n in noises]):
+                li, la, _, _ = trainer.model(image, audio)
+            trainer.step(li + la)
+
+    full = fresh(); run(full, 4)                                   # uninterrupted
+    first = fresh(); run(first, 2)
+    mgr = CheckpointManager(first.module_dict(), str(tmp_path), epochs=10, save_freq=1)
+    mgr.checkpoint(1, {"epoch": 1, "best_loss": 0.5}, is_best=True)
+    for name in ("checkpoint_latest.pth", "checkpoint_best.pth", "checkpoint_0001.pth"):
+        assert (tmp_path / name).is_file()
+    ckpt = torch.load(tmp_path / "checkpoint_latest.pth", map_location="cpu", weights_only=False)
+    assert set(ckpt) == {"state_dict", "optimizer", "n_steps", "epoch", "best_loss"} and int(ckpt["n_steps"]) == 2
+    assert set(ckpt["state_dict"]) == set(sd) and all(not v.is_cuda for v in ckpt["state_dict"].values())
+
+    # the optimizer entry is torch.optim.AdamW's: a stock optimizer over same-shaped parameters loads it ...
+    clones = [[torch.nn.Parameter(p.detach().cpu().clone()) for p in g["params"]] for g in first.optimizer.param_groups]
+    stock = torch.optim.AdamW([{"params": ps} for ps in clones], lr=1e-3, betas=(0.9, 0.95))
+    stock.load_state_dict(ckpt["optimizer"])
+    st0 = stock.state[clones[1][0]]
+    ours0 = first.optimizer.state[first.optimizer.param_groups[1]["params"][0]]
+    assert float(st0["step"]) == 2 and torch.equal(st0["exp_avg"], ours0["exp_avg"].cpu()) and torch.equal(st0["exp_avg_sq"], ours0["exp_avg_sq"].cpu())
+    # ... and what the stock optimizer writes loads back
+    first.optimizer.load_state_dict(stock.state_dict())
+    assert first.optimizer.n_steps == 2
+
+    resumed = fresh()
+    mgr2 = CheckpointManager(resumed.module_dict(), str(tmp_path), epochs=10)
+    epoch, metrics = mgr2.resume()
+    assert epoch == 1 and metrics == {"best_loss": 0.5} and int(resumed.n_steps) == 2 and resumed.optimizer.n_steps == 2
+    # state right after the resume is bit-identical to the run that wrote the file
+    assert torch.equal(resumed.store.flat_p, first.store.flat_p)
+    assert torch.equal(resumed.optimizer.flat_m, first.optimizer.flat_m) and torch.equal(resumed.optimizer.flat_v, first.optimizer.flat_v)
+    assert torch.equal(resumed.optimizer.scal[:2].cpu(), first.optimizer.scal[:2].cpu())
+    run(resumed, 2)
+    # and it continues like the uninterrupted run: the only differences are beta^t rebuilt as b ** t instead of t f32
+    # multiplications (1 ulp) and, on the GPU, the order of the f32 atomics in the weight gradients
+    p0 = fresh().store.flat_p
+    num, den = float((resumed.store.flat_p - full.store.flat_p).norm()), float((full.store.flat_p - p0).norm())
+    assert num <= 2e-3 * den, (num, den)
+    assert int(resumed.n_steps) == int(full.n_steps) == 4 and resumed.optimizer.n_steps == 4
+
+
+def test_checkpoint_manager_resume(monkeypatch, tmp_path):
+    cpu_kernels.install(monkeypatch)
+    _checkpoint_resume_case("cpu", tmp_path)
