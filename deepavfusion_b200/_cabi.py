@@ -116,6 +116,10 @@ SIGNATURES = {
     "davf_batchnorm1d_bwd": (i, [vp, vp, vp, vp, i, i, i, vp, vp]),
     "davf_head_fwd": (i, [vp, vp, vp, i, i, i, vp, vp]),
     "davf_head_bwd": (i, [vp, vp, vp, i, i, i, vp, vp, vp, vp]),
+    "davf_logmel_workspace_bytes": (i64, []),
+    "davf_logmel_init": (i, [vp, i, i, i, i, vp]),
+    "davf_logmel_fwd": (i, [vp, vp, vp, vp, i, i, i, i, f, vp, vp]),
+    "davf_image_normalize_u8": (i, [vp, vp, i, i, i, i, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]),
     "davf_scale_rows_add": (i, [vp, vp, vp, i, i64, i, vp, vp]),
     "davf_scale_rows": (i, [vp, vp, i, i64, i, vp, vp, vp]),
 }

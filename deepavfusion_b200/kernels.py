@@ -502,6 +502,41 @@ def head_bwd(dy: Tensor, x: Tensor, W: Tensor, dW: Optional[Tensor], db: Optiona
 
 
 # --------------------------------------------------------------------------------------------
+# input stage: log-mel + frame normalisation
+# --------------------------------------------------------------------------------------------
+def logmel_workspace(sample_rate: int, n_fft: int, hop: int, n_mels: int, device) -> Tensor:
+    """Device tables of the log-mel kernel (twiddles, window, mel filter bank), filled once."""
+    ws = torch.empty(int(_cabi.lib().davf_logmel_workspace_bytes()), dtype=torch.uint8, device=device)
+    check(_cabi.lib().davf_logmel_init(_ptr(ws), sample_rate, n_fft, hop, n_mels, _stream()), "davf_logmel_init")
+    return ws
+
+
+def logmel_fwd(ws: Tensor, wave: Tensor, gain_db: Optional[Tensor], n_mels: int, frames: int, eps: float) -> Tensor:
+    """wave f32 or int16 PCM [B, T] -> log-mel f32 [B, 1, n_mels, frames]."""
+    if not wave.is_cuda:
+        raise RuntimeError("wave: expected a CUDA tensor (the sm_100a kernels have no CPU path)")
+    assert wave.dim() == 2 and wave.is_contiguous() and wave.dtype in (torch.float32, torch.int16)
+    B, T = wave.shape
+    out = torch.empty(B, 1, n_mels, frames, dtype=torch.float32, device=wave.device)
+    is16 = wave.dtype == torch.int16
+    check(_cabi.lib().davf_logmel_fwd(_ptr(ws), _ptr(None if is16 else wave), _ptr(wave if is16 else None),
+                                     _ptr(None if gain_db is None else _need(gain_db, torch.float32, "gain_db")), B, T, n_mels, frames, float(eps),
+                                     _ptr(out), _stream()), "davf_logmel_fwd")
+    return out
+
+
+def image_normalize_u8(img: Tensor, mean: Sequence[float], std: Sequence[float]) -> Tensor:
+    """uint8 [B, H, W, C] -> f32 [B, C, H, W] normalised."""
+    _need(img, torch.uint8, "img")
+    B, H, W, Cc = img.shape
+    out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=img.device)
+    m = (C.c_float * Cc)(*[float(x) for x in mean])
+    sd = (C.c_float * Cc)(*[float(x) for x in std])
+    check(_cabi.lib().davf_image_normalize_u8(_ptr(img), _ptr(out), B, H, W, Cc, m, sd, _stream()), "davf_image_normalize_u8")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # stochastic depth (fine-tuning only)
 # --------------------------------------------------------------------------------------------
 def scale_rows_add(res: Tensor, y: Tensor, scale: Tensor, rows_per_sample: int) -> Tensor:

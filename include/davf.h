@@ -249,6 +249,23 @@ int davf_decoder_assemble_bwd(const float* dseq, const int64_t* ids_keep, const 
                               davf_bf16* de, davf_bf16* def_, float* dmask_token, float* dpos,
                               int B, int nK, int nF, int L, int D, davf_stream_t s);
 
+/* ---- input stage: log-mel spectrograms and frame normalisation on the GPU -------------------------
+ * Replaces the CPU data-loader transforms of train.py:44-54: torchaudio MelSpectrogram(sample_rate, n_fft = 800,
+ * hop_length = 250, n_mels) with torchaudio's defaults (periodic Hann window, centre / reflect padding, power 2, HTK mel
+ * scale, no filter normalisation) followed by util/audio_transforms.py Log (log10(x + eps)), optionally preceded by
+ * RandomVol's gain + clamp (audio_transforms.py:8-18) with the per-clip gain drawn by the caller; and torchvision
+ * ToTensor + Normalize.  int16 PCM / uint8 frames cross PCIe instead of fp32 tensors.
+ * workspace: davf_logmel_workspace_bytes() bytes of device memory owned by the caller, filled once by davf_logmel_init
+ * (twiddles, window, filter bank).  wave: exactly one of wave_f32 / wave_i16 (PCM, / 32768), [B, T]; gain_db f32 [B] or
+ * NULL; out f32 [B, 1, n_mels, frames], frames <= T / hop + 1 (datasets.py:242 keeps T / hop). */
+int64_t davf_logmel_workspace_bytes(void);
+int davf_logmel_init(void* workspace, int sample_rate, int n_fft, int hop, int n_mels, davf_stream_t s);
+int davf_logmel_fwd(const void* workspace, const float* wave_f32, const int16_t* wave_i16, const float* gain_db, int B, int T,
+                    int n_mels, int frames, float eps, float* out, davf_stream_t s);
+/* src u8 [B, H, W, C] (device) -> dst f32 [B, C, H, W] = (src / 255 - mean[c]) / std[c]; mean / std are HOST arrays of C floats. */
+int davf_image_normalize_u8(const uint8_t* src, float* dst, int B, int H, int W, int C, const float* mean, const float* std_,
+                            davf_stream_t s);
+
 /* ---- K12: normalised masked patch-MSE --------------------------------------------------------
  * Replaces avmae.py:201-214 (patchify) + :183-198 (forward_loss).  img f32 [B,C,H,W];
  * pred f32 rows: patch (b,l) is at pred + (b*pred_G + pred_off + l)*P, P = p*p*C (in-patch order

@@ -114,3 +114,17 @@ def test_classifier_oracle_matches_reference_fixture():
         np.testing.assert_allclose(mine, z[f"{tag}_grad_norms"], rtol=1e-4, atol=1e-7)
         for k, v in stats.items():
             np.testing.assert_allclose(v.numpy(), z[f"{tag}_{k}"], rtol=1e-5, atol=1e-7)
+
+
+def test_logmel_oracle_matches_torchaudio_fixture():
+    """The front-end oracle (oracle/logmel_oracle.py) against the fixture written from the reference's own torchaudio
+    pipeline (train.py:50-54, datasets.py:242) by oracle/make_golden_logmel.py."""
+    from oracle import logmel_oracle as L
+    z = np.load(os.path.join(GOLD, "logmel.npz"))
+    wave = L.make_wave()
+    assert np.array_equal(wave[:, :64].numpy(), z["wave_head"])
+    out = L.log_mel(wave, torch.from_numpy(z["gain_db"]))
+    ref = torch.from_numpy(z["logmel"])
+    assert out.shape == ref.shape == (3, 1, 128, 192)
+    assert float((out - ref).abs().max()) < 2e-3          # torchaudio evaluates in f32: its quiet bands carry ~1e-3 of rounding
+    assert float((out - ref).abs()[ref > ref.amax(dim=2, keepdim=True) - 4.0].max()) < 3e-4      # within 40 dB of the frame's loudest band
