@@ -83,8 +83,6 @@ SIGNATURES = {
     "davf_last_error": (C.c_char_p, []),
     "davf_version": (i, []),
     "davf_device_sm": (i, []),
-    "davf_set_gemm_impl": (i, [i]),
-    "davf_get_gemm_impl": (i, []),
     "davf_set_gemm_2cta": (i, [i]),
     "davf_set_gemm_sms": (i, [i]),
     "davf_set_attn_impl": (i, [i]),

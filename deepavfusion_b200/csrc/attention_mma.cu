@@ -451,8 +451,6 @@ static int launch_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   return launch_bwd_nw<DQK, DV, 8>(a, st);
 }
 
-int attn_simt_fwd(const davf_attn_fwd_args* a, cudaStream_t st);
-int attn_simt_bwd(const davf_attn_bwd_args* a, cudaStream_t st);
 // tcgen05 / TMEM / TMA kernels (attention_tc.cu): every problem with more than 16 query rows and head dim 64 / 32
 bool attn_tc_fwd_ok(const davf_attn_fwd_args& a);
 bool attn_tc_bwd_ok(const davf_attn_bwd_args& a);
@@ -489,7 +487,7 @@ static int zero_dead_rows(const davf_attn_bwd_args& a, cudaStream_t st) {
 using namespace davf;
 
 extern "C" int davf_set_attn_impl(int impl) {
-  DAVF_CHECK_ARG(impl >= 0 && impl <= 2, "set_attn_impl: %d", impl);
+  DAVF_CHECK_ARG(impl == 0 || impl == 2, "set_attn_impl: %d (0 = default dispatch, 2 = mma.sync everywhere)", impl);
   g_attn_impl.store(impl);
   return DAVF_OK;
 }
@@ -502,7 +500,6 @@ extern "C" int davf_attention_fwd(const davf_attn_fwd_args* a, davf_stream_t s) 
   DAVF_CHECK_ARG((((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) & 15) == 0 && ((uintptr_t)a->o & 3) == 0, "attention_fwd: q/k/v must be 16-byte aligned");
   if (a->B == 0) return DAVF_OK;
   cudaStream_t st = as_stream(s);
-  if (g_attn_impl.load() == 1) return attn_simt_fwd(a, st);
   if (g_attn_impl.load() == 0 && attn_tc_fwd_ok(*a)) return attn_tc_fwd(*a, st);
   if (a->dqk == 64 && a->dv == 64) return launch_fwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_fwd<32, 32>(*a, st);
@@ -525,7 +522,6 @@ extern "C" int davf_attention_bwd(const davf_attn_bwd_args* a, davf_stream_t s) 
   if (g_attn_impl.load() == 0 && attn_tc_bwd_ok(*a)) return attn_tc_bwd(*a, st);     // (zero-fills the dead rows itself)
   if (a->dq_dead_rows > 0)
     if (int rc = zero_dead_rows(*a, st)) return rc;
-  if (g_attn_impl.load() == 1) return attn_simt_bwd(a, st);
   if (a->dqk == 64 && a->dv == 64) return launch_bwd<64, 64>(*a, st);
   if (a->dqk == 32 && a->dv == 32) return launch_bwd<32, 32>(*a, st);
   if (a->dqk == 16 && a->dv == 64) return launch_bwd<16, 64>(*a, st);

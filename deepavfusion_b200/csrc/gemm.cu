@@ -1,18 +1,8 @@
-// davf_gemm: argument validation + dispatch (tcgen05 kernel by default, SIMT checker on request).
+// davf_gemm: argument validation + dispatch to the tcgen05 kernels.
 #include "gemm_epilogue.cuh"
-
-namespace davf {
-static std::atomic<int> g_gemm_impl{0};
-}
 
 using namespace davf;
 
-extern "C" int davf_set_gemm_impl(int impl) {
-  DAVF_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: %d", impl);
-  g_gemm_impl.store(impl);
-  return DAVF_OK;
-}
-extern "C" int davf_get_gemm_impl(void) { return g_gemm_impl.load(); }
 namespace davf { int gemm_set_2cta(int on); int gemm_set_sms(int n); }
 extern "C" int davf_set_gemm_sms(int n) { return davf::gemm_set_sms(n); }
 extern "C" int davf_set_gemm_2cta(int on) { return davf::gemm_set_2cta(on); }
@@ -40,7 +30,6 @@ static int validate_gemm(const davf_gemm_args* a) {
 extern "C" int davf_gemm(const davf_gemm_args* a, davf_stream_t s) {
   if (int rc = validate_gemm(a)) return rc;
   if (a->M == 0) return DAVF_OK;
-  if (g_gemm_impl.load() == 1) return gemm_simt_launch(*a, as_stream(s));
   return gemm_tc_launch(*a, as_stream(s));
 }
 
@@ -56,11 +45,6 @@ extern "C" int davf_gemm_grouped(const davf_gemm_args* a, int count, davf_stream
   }
   if (n == 0) return DAVF_OK;
   cudaStream_t st = as_stream(s);
-  if (g_gemm_impl.load() == 1) {
-    for (int p = 0; p < n; ++p)
-      if (int rc = gemm_simt_launch(live[p], st)) return rc;
-    return DAVF_OK;
-  }
   if (n == 1) return gemm_tc_launch(live[0], st);
   return gemm_tc_launch_grouped(live, n, st);
 }

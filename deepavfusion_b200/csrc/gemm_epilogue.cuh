@@ -83,7 +83,7 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, int64_t m, int6
   }
 }
 
-int gemm_simt_launch(const davf_gemm_args& a, cudaStream_t st);
+int gemm_simt_launch(const davf_gemm_args& a, cudaStream_t st);      // tests/check/libdavf_check.so only (CUDA-core checker)
 int gemm_tc_launch(const davf_gemm_args& a, cudaStream_t st);
 int gemm_tc_launch_grouped(const davf_gemm_args* a, int count, cudaStream_t st);   // count <= DAVF_GEMM_MAX_GROUP, one layout class
 

@@ -584,10 +584,6 @@ def set_pdl(on: bool) -> None:
     check(_cabi.lib().davf_set_pdl(int(on)), "davf_set_pdl")
 
 
-def set_gemm_impl(impl: int) -> None:
-    check(_cabi.lib().davf_set_gemm_impl(impl), "davf_set_gemm_impl")
-
-
 def set_gemm_2cta(on: bool) -> None:
     check(_cabi.lib().davf_set_gemm_2cta(int(on)), "davf_set_gemm_2cta")
 

@@ -4,8 +4,8 @@
 // loop and no HBM round trip for the score matrix.  Strided q/k/v/o addressing lets the kernel read
 // packed qkv buffers, query sub-ranges (live rows only) and write packed dqkv buffers directly.
 //
-// This file is the CUDA-core (f32 FMA) CHECKER implementation, selected with davf_set_attn_impl(1);
-// the default path is the tensor-core kernel in attention_mma.cu.
+// This file is the CUDA-core (f32 FMA) CHECKER implementation (tests/check/libdavf_check.so, test infrastructure);
+// the product kernels are csrc/attention_tc.cu (tcgen05) and csrc/attention_mma.cu (mma.sync).
 #include "common.cuh"
 
 namespace davf {

@@ -1,6 +1,6 @@
 // SIMT (CUDA-core) GEMM with the same argument struct and epilogue as the tcgen05 kernel.
 // It is the on-device CHECKER for the tensor-core kernel (tests compare the two on the GPU) and a
-// debug switch (davf_set_gemm_impl(1)); it is never selected by default.
+// (tests/check/libdavf_check.so; test infrastructure -- the product library does not contain it).
 #include "gemm_epilogue.cuh"
 
 namespace davf {

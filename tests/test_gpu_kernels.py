@@ -1,5 +1,6 @@
 """-m gpu: every CUDA kernel of libdavf_sm100.so against its torch emulation (tests/cpu_kernels.py,
 which the CPU suite in turn checks against the oracle) on the same seeded inputs, through the C ABI."""
+import contextlib
 import os
 import subprocess
 import sys
@@ -124,7 +125,10 @@ def rnd(*s, seed=0, dtype=torch.float32):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(*s, generator=g).to(dtype).cuda()
 impl = int(sys.argv[1])
-K.set_gemm_impl(impl)
+if impl == 1:                      # the CUDA-core checker kernels (tests/check/libdavf_check.so) behind the same wrappers
+    import check_lib
+    _route = check_lib.routed("gemm")
+    _route.__enter__()
 fails = 0
 def check(name, got, ref, rtol=2e-2, atol=2e-2):
     global fails
@@ -274,13 +278,17 @@ def test_gemm_all_modes(impl, streamk):
 @pytest.mark.parametrize("impl", [0, 2, 1], ids=["tcgen05", "mma", "simt"])
 def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
     """impl 0 = product dispatch: tcgen05 / TMEM / TMA kernels for > 16 query rows at head dim 64 / 32 (asserted through the
-    per-family launch counter), mma.sync kernels for the tiny fusion-token problems; 2 = mma.sync everywhere; 1 = CUDA-core checker."""
+    per-family launch counter), mma.sync kernels for the tiny fusion-token problems; 2 = mma.sync everywhere; 1 = the CUDA-core
+    checker kernels of tests/check/libdavf_check.so behind the same wrappers (checks the checker against the torch emulation)."""
     if impl == 1 and B * H * Nq * Nk > 3_000_000:
         pytest.skip("checker kernel: small cases only")
-    K.set_attn_impl(impl)
+    import check_lib
+    ctx = check_lib.routed("attention") if impl == 1 else contextlib.nullcontext()
+    K.set_attn_impl(0 if impl == 1 else impl)
     try:
         n0 = K.launch_count_kind(K.KIND_ATTN_TC)
-        _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
+        with ctx:
+            _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
         tc = K.launch_count_kind(K.KIND_ATTN_TC) - n0
         eligible = impl == 0 and Nq > 16 and dqk == dv and dqk in (32, 64)
         packed = dqk == dv and Nq + skip <= Nk and skip > 0

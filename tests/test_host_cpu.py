@@ -191,7 +191,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = _cabi.lib()
     assert lib.davf_version() == 1
     # argument validation happens before any CUDA call
-    assert lib.davf_set_gemm_impl(7) == -1 and b"set_gemm_impl" in lib.davf_last_error()
+    assert lib.davf_set_attn_impl(7) == -1 and b"set_attn_impl" in lib.davf_last_error()
     assert lib.davf_mask_rank(None, 1, 4, 9, None, None, None, None) == -1
 
 
