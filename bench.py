@@ -396,7 +396,7 @@ def nccl_summary():
     ver = pick("NCCL version")
     chans = pick("coll channels", "collnet channels", "nvls channels", " channels, ")
     nvls = pick("NVLS")
-    algos = pick("Algo", "algo")
+    algos = [l for l in pick("Algo", "algo") if "->" in l]          # "AllReduce: N Bytes -> Algo RING proto SIMPLE channel{Lo..Hi}={0..31}"
     return dict(version=ver[:1], channels=chans[:2], nvls=bool(nvls), nvls_lines=nvls[:2], tuning=sorted(set(algos))[:6], log_lines=len(keep))
 
 

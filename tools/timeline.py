@@ -18,14 +18,27 @@ g = GraphedTrainStep(trainer, img, aud, warmup=2)
 for _ in range(3): g(img, aud)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
+NSTEPS = int(os.environ.get("DAVF_TIMELINE_STEPS", "1"))      # > 1: back-to-back replays, the host running ahead as in training
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    g(img, aud)
+    for _ in range(NSTEPS):
+        g(img, aud)
     torch.cuda.synchronize()
 os.makedirs("gpurun_out", exist_ok=True)
 prof.export_chrome_trace("gpurun_out/timeline.json")
 ev = json.load(open("gpurun_out/timeline.json"))["traceEvents"]
 ks = [e for e in ev if e.get("cat") == "kernel"]
 ks.sort(key=lambda e: e["ts"])
+if NSTEPS > 1:
+    # steady state: the gap between the last kernel of one replay and the first kernel of the next (the graph's head), then
+    # keep the LAST replay for the per-stream summary below
+    starts = [i for i, e in enumerate(ks) if "distribution_elementwise" in e["name"]][::2]      # first rand kernel of each step
+    gaps = []
+    for i in starts[1:]:
+        prev_end = max(e["ts"] + e["dur"] for e in ks[:i] if "Fill" not in e["name"] or e["ts"] < ks[i]["ts"] - 2000)
+        gaps.append((ks[i]["ts"] - prev_end) / 1e3)
+    print("steady-state head gaps between consecutive replays (ms):", [round(x, 3) for x in gaps])
+    print("step periods (ms):", [round((ks[b]["ts"] - ks[a]["ts"]) / 1e3, 3) for a, b in zip(starts, starts[1:])])
+    ks = ks[starts[-1]:]
 t0 = ks[0]["ts"]; t1 = max(e["ts"] + e["dur"] for e in ks)
 out = [f"kernels {len(ks)}  span {(t1 - t0) / 1e3:.2f} ms"]
 by = collections.defaultdict(list)
