@@ -671,7 +671,7 @@ def run_ours(args):
         dp = dp_checks(trainer, cfg, dev, rank, world)
         if rank == 0:
             dp["nccl"] = nccl_summary()
-            dp["gemm_sms"] = K.set_gemm_sms(148 - int(os.environ.get("DAVF_COMM_SMS", "32")))
+            dp["gemm_sms_backward"] = 148 - int(os.environ.get("DAVF_COMM_SMS", "32"))      # forward launches use all 148
 
     # ---- roofline of the dominant kernel + baselines (rank 0) -----------------------------------------
     roof, base, eager = None, None, None

@@ -52,9 +52,9 @@ class Trainer:
             if (self.distributed or overlap_opt) else None
         if self.distributed:
             self.broadcast_parameters()
-            if self.store.flat_g.is_cuda:       # leave SMs to the NCCL kernels that run under backward (see davf_set_gemm_sms)
-                from .. import kernels as K
-                K.set_gemm_sms(148 - int(os.environ.get("DAVF_COMM_SMS", "32")))
+            # SMs left to the NCCL kernels that run under backward (see davf_set_gemm_sms).  Only BACKWARD launches of the
+            # final micro-step overlap the bucket all-reduces: forward (and accumulate-only) launches keep the whole machine.
+            self._comm_sms = int(os.environ.get("DAVF_COMM_SMS", "32")) if self.store.flat_g.is_cuda else 0
         world = dist_utils.get_world_size() if self.distributed else 1
         if self.optimizer is not None:
             self.optimizer.set_grad_scale(1.0 / (self.accum_iter * world))
@@ -98,7 +98,15 @@ class Trainer:
             if _fuse_optimizer and self.sync.enabled and self.sync.optimizer is not None:
                 self.optimizer.begin_step(sync_hp=_sync_hp)              # the step is applied bucket by bucket during backward
                 self.sync.fuse_optimizer = True
-        loss.backward()
+        comm_sms = getattr(self, "_comm_sms", 0) if (self.sync is not None and self.sync.enabled and self.distributed) else 0
+        if comm_sms:
+            from .. import kernels as K
+            K.set_gemm_sms(148 - comm_sms)
+        try:
+            loss.backward()
+        finally:
+            if comm_sms:
+                K.set_gemm_sms(148)
         self.store.join_side_streams(torch.cuda.current_stream() if self.store.flat_g.is_cuda else None)
         if self.sync is not None:
             self.sync.finish()
