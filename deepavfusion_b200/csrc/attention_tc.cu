@@ -243,45 +243,38 @@ __global__ void __launch_bounds__(192, 2) attn_tc_fwd_kernel(const __grid_consta
       const bool live = qt * 128 + quad * 32 < p.Nq;               // warp-uniform: this warp owns at least one real query
       mbar_wait(s_ready, it & 1);
       tc_fence_after();
-      float mx = -INFINITY, l = 0.f;
+      float mx = -INFINITY, l = 0.f, m2 = 0.f;
       const int nch = (nk16 + 31) >> 5;                            // 32-column chunks of the score row
       uint32_t va[32], vb[32];
+      // Softmax is shift-invariant, and bf16 / f32 share one exponent range, so the shift only has to keep 2^(s sl - m2)
+      // finite: ANY m2 within +-64 of the true row maximum gives the same P to the last bit of its mantissa.  TMEM reads
+      // run at 64 B/clk/SM, i.e. a second pass over the 128 x Nk score tile costs as much as all its ex2 -- so the
+      // shift is the maximum of the FIRST 32 columns (a lower bound of the row maximum, hence p >= 1 somewhere: no
+      // underflow), the exact maximum is tracked on the fly, and only a row whose maximum exceeds the estimate by more
+      // than 64 (p > 2^64; never seen on real activations) repeats the pass with the exact value.  LSE = m2 + log2(l)
+      // holds for any shift.
       if (live) {
-        // pass 1: row max.  The TMEM load of chunk c + 1 is in flight while chunk c is reduced.
-        auto reduce_max = [&](const uint32_t (&v)[32], int c) {
-          if (c * 32 + 32 <= p.Nk) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx = (c * 32 + e < p.Nk) ? fmaxf(mx, __uint_as_float(v[e])) : mx;
-          }
-        };
         tmem_ld_32x32b_x32_issue(trow, va);
         tmem_ld_wait(va);
-        for (int c = 0; c < nch; c += 2) {
-          if (c + 1 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 1) * 32, vb);
-          reduce_max(va, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait(vb);
-            if (c + 2 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 2) * 32, va);
-            reduce_max(vb, c + 1);
-            if (c + 2 < nch) tmem_ld_wait(va);
-          }
-        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = (e < p.Nk) ? fmaxf(mx, __uint_as_float(va[e])) : mx;
+        m2 = mx * sl;
       }
-      const float m2 = mx * sl;
       if (it > 0) mbar_wait(stg_free, (it - 1) & 1);               // the TMA store of the previous item has read X (P's last tile when NKP = 256)
       if (live) {
-        // pass 2: p = 2^(s sl - m2), row sum, bf16 P tile (Q and K are dead: S is complete)
+        // p = 2^(s sl - m2), row sum, bf16 P tile (Q and K are dead: S is complete)
         auto emit = [&](const uint32_t (&v)[32], int c) {
           float pr[32];
           if (c * 32 + 32 <= p.Nk) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) pr[e] = ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2));
+            for (int e = 0; e < 32; ++e) { mx = fmaxf(mx, __uint_as_float(v[e])); pr[e] = ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2)); }
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) pr[e] = (c * 32 + e < p.Nk) ? ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2)) : 0.f;
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = c * 32 + e < p.Nk;
+              mx = ok ? fmaxf(mx, __uint_as_float(v[e])) : mx;
+              pr[e] = ok ? ex2_tc(fmaf(__uint_as_float(v[e]), sl, -m2)) : 0.f;
+            }
           }
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -294,17 +287,24 @@ __global__ void __launch_bounds__(192, 2) attn_tc_fwd_kernel(const __grid_consta
             sts_128(chunk + (((j0 + j) ^ sw) << 4), pack_bf16x2(pr[8 * j], pr[8 * j + 1]), pack_bf16x2(pr[8 * j + 2], pr[8 * j + 3]),
                     pack_bf16x2(pr[8 * j + 4], pr[8 * j + 5]), pack_bf16x2(pr[8 * j + 6], pr[8 * j + 7]));
         };
-        tmem_ld_32x32b_x32_issue(trow, va);
-        tmem_ld_wait(va);
-        for (int c = 0; c < nch; c += 2) {
-          if (c + 1 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 1) * 32, vb);
-          emit(va, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait(vb);
-            if (c + 2 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 2) * 32, va);
-            emit(vb, c + 1);
-            if (c + 2 < nch) tmem_ld_wait(va);
+        auto sweep = [&](bool first_loaded) {                       // the TMEM load of chunk c + 1 is in flight while chunk c is processed
+          if (!first_loaded) { tmem_ld_32x32b_x32_issue(trow, va); tmem_ld_wait(va); }
+          for (int c = 0; c < nch; c += 2) {
+            if (c + 1 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 1) * 32, vb);
+            emit(va, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait(vb);
+              if (c + 2 < nch) tmem_ld_32x32b_x32_issue(trow + (c + 2) * 32, va);
+              emit(vb, c + 1);
+              if (c + 2 < nch) tmem_ld_wait(va);
+            }
           }
+        };
+        sweep(true);
+        if (__any_sync(0xffffffffu, mx * sl - m2 > 64.0f)) {        // (warp-uniform) exact repeat: the row maximum is known now
+          m2 = mx * sl;
+          l = 0.f;
+          sweep(false);
         }
       }
       fence_async_smem();                                          // generic-proxy P writes -> visible to tcgen05.mma

@@ -332,6 +332,31 @@ def _attention_case(K, B, H, Nq, Nk, dqk, dv, skip):
         close(dqkv[:, :, 2], edv, 3e-2, 3e-2, "dv (packed)")
 
 
+def test_attention_tc_large_logits_repeat_path(K):
+    """The tcgen05 forward shifts the softmax by the maximum of the FIRST 32 keys and repeats a row with the exact maximum
+    only when that estimate is off by more than 2^64: logits with a standard deviation of ~100 (scale 1, |q|, |k| ~ 3 sqrt(d))
+    take the repeat path on most rows; the result and the LSE must still match the reference."""
+    B, H, Nq, Nk, d = 3, 4, 130, 200, 64
+    q, k, v = rnd(B, Nq, H, d, seed=41, dtype=bf16) * 3, rnd(B, Nk, H, d, seed=42, dtype=bf16) * 3, rnd(B, Nk, H, d, seed=43, dtype=bf16)
+    k[:, 150] *= 4                                         # a far outlier key behind the first chunk
+    n0 = K.launch_count_kind(K.KIND_ATTN_TC)
+    o, lse = K.attention_fwd(q, k, v, 1.0)
+    assert K.launch_count_kind(K.KIND_ATTN_TC) == n0 + 1
+    eo, else_ = E.attention_fwd(q.cpu(), k.cpu(), v.cpu(), 1.0)
+    assert bool(torch.isfinite(o.float()).all()) and bool(torch.isfinite(lse).all())
+    close(o, eo, 3e-2, 3e-2, "attn o (large logits)")
+    assert float((lse.cpu() - else_).abs().max()) <= 2e-3 * float(else_.abs().max())
+    # and the backward consumes that LSE
+    do = rnd(B, Nq, H, d, seed=44, dtype=bf16)
+    dq, dk, dvv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    K.attention_bwd(q, k, v, do, lse, 1.0, dq, dk, dvv, o=o)
+    edq, edk, edv = torch.zeros(q.shape, dtype=bf16), torch.zeros(k.shape, dtype=bf16), torch.zeros(v.shape, dtype=bf16)
+    E.attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), lse.cpu(), 1.0, edq, edk, edv, o=o.cpu())
+    for got, ref, name in ((dq, edq, "dq"), (dk, edk, "dk"), (dvv, edv, "dv")):
+        rel = float((got.float().cpu() - ref.float()).norm() / (ref.float().norm() + 1e-30))
+        assert rel < 3e-2, (name, rel)
+
+
 # ---------------------------------------------------------------- decoder assembly / loss / optimizer
 def test_decoder_assemble(K):
     B, nK, nF, L, D = 4, 49, 32, 196, 512
