@@ -40,12 +40,18 @@ __host__ __device__ constexpr bool direct_epi(int epi) {   // compile-time epilo
   return epi >= 0;
 }
 constexpr uint32_t kTmaBox = 4096;                     // one TMA box of the direct epilogue: 32 rows x 128 B (64 bf16), SW128
-__host__ __device__ constexpr uint32_t staging_bytes(int epi, int epi_warps) { return direct_epi(epi) ? epi_warps * 2u * kTmaBox : staging_bytes(epi_warps); }
+// epilogues with a matrix operand (f32 residual: EPI_RES = 16, saved gelu': EPI_DGELU = 4) run a ring of three boxes per warp
+__host__ __device__ constexpr bool ring_epi(int epi) { return epi >= 0 && (epi & (16 | 4)) != 0; }
+// (two for the single-CTA 256-wide tile, whose 48 KB pipeline stages leave no room for a third)
+__host__ __device__ constexpr uint32_t ring_boxes(int bn, int cg) { return (bn == 256 && cg == 1) ? 2u : 3u; }
+__host__ __device__ constexpr uint32_t staging_bytes(int epi, int epi_warps, int bn, int cg) {
+  return direct_epi(epi) ? epi_warps * (ring_epi(epi) ? ring_boxes(bn, cg) : 2u) * kTmaBox : staging_bytes(epi_warps);
+}
 __host__ __device__ constexpr uint32_t ones_bytes(int epi) { return (epi >= 0 && (epi & 128) == 0) ? 0u : 2048u; }   // all-ones B tile of the row-sum MMA
 // pipeline depth: what the caller asks for, capped by what fits next to the epilogue staging in 227 KB
 __host__ __device__ constexpr int fit_stages(int want, int epi, int ew, int bn, int cg) {
   const int stage = 128 * 64 * 2 + (bn / cg) * 64 * 2;
-  const int avail = 232448 - 1024 - 16 - 8 * (2 * want + 5 + ew) - (int)ones_bytes(epi) - (int)staging_bytes(epi, ew);
+  const int avail = 232448 - 1024 - 16 - 8 * (2 * want + 5 + 3 * ew) - (int)ones_bytes(epi) - (int)staging_bytes(epi, ew, bn, cg);
   return avail / stage < want ? avail / stage : want;
 }
 
@@ -154,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 atoms need 1024 B alignment
   const uint32_t stage_base = smem_base + STAGES * STAGE_BYTES;          // epilogue staging, kStagingBytes
-  const uint32_t ones_base = stage_base + staging_bytes(EPI, EW);              // 1024-byte aligned, kOnesBytes
+  const uint32_t ones_base = stage_base + staging_bytes(EPI, EW, BN, CG);              // 1024-byte aligned, kOnesBytes
   const uint32_t bar_base = ones_base + ones_bytes(EPI);
   bool want_rowsum = false;
 #pragma unroll
@@ -165,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
-  auto aux_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 5 + w); };     // direct epilogue: TMA loads of the saved gelu'
+  auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 5 + 3 * w + b); };     // TMA loads of the epilogue's matrix operand: 3 boxes per warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -185,7 +191,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EW * CG);     // the leader's barrier collects the epilogue warps of both CTAs
     }
-    for (int w = 0; w < EW; ++w) mbar_init(aux_bar(w), 1);
+    for (int w = 0; w < EW; ++w)
+      for (int b = 0; b < 3; ++b) mbar_init(aux_bar(w, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (ones_bytes(EPI) > 0) if (want_rowsum) {      // bf16 1.0 everywhere: layout-agnostic B operand
@@ -315,6 +322,134 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
         if (dbg && t == 0 && leader) dbg[3] = clock64();
       }
     }
+  } else if constexpr (ring_epi(EPI)) {
+    // ===================== TMA epilogue with a matrix operand: f32 residual (proj / fc2) or saved gelu' (fc2 dgrad) =====================
+    // As below, but the operand box is loaded by TMA TWO groups ahead into a ring of three boxes per warp and the result
+    // is computed IN PLACE in the box the operand arrived in, which then leaves by a TMA store.  With one operand box
+    // the L2 / HBM latency of every box load (~1 k clk) was exposed once per 32-row x 128-byte group, i.e. the
+    // epilogue of a K = 512 tile took longer than its MMAs.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    constexpr int SLICE = BN / (EW / 4);
+    constexpr bool kBias = (EPI & EPI_BIAS) != 0, kMul = (EPI & EPI_DGELU) != 0, kRes = (EPI & EPI_RES) != 0, kF32 = (EPI & EPI_BF16) == 0;
+    static_assert((kRes && kF32 && !kMul) || (kMul && !kF32 && !kRes), "ring epilogue: f32 + residual, or bf16 x gelu'");
+    static_assert((EPI & (EPI_GELU | EPI_AUX | EPI_RED | EPI_ROWSUM)) == 0, "ring epilogue: no second output / reduction");
+    constexpr int GW = kF32 ? 32 : 64;                  // columns per box (128 bytes per row)
+    constexpr int NGRP = SLICE / GW;
+    static_assert(SLICE % GW == 0, "TMA epilogue works on whole boxes");
+    constexpr int NBOX = (int)ring_boxes(BN, CG);       // operand boxes in flight: NBOX - 1 groups ahead
+    const uint32_t boxes = stage_base + (uint32_t)ew * (uint32_t)NBOX * kTmaBox;
+    const uint32_t my_row = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+    // load cursor: the next ACTIVE group (tile lt, group lg) whose operand box has not been requested yet
+    int lt = cluster_id - num_clusters, lg = NGRP - 1, l_p = 0, l_m0 = 0, l_nbase = 0;
+    bool l_ok = false, l_valid = true;
+    int issued = 0, done = 0;
+    auto lc_advance = [&]() {
+      while (true) {
+        if (++lg == NGRP) {
+          lg = 0;
+          lt += num_clusters;
+          if (lt >= num_tiles) { l_valid = false; return; }
+          int tl, m_blk, n_blk, sp, kb0, kb1;
+          locate(lt, l_p, tl);
+          gp.ts[l_p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+          l_m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;
+          l_nbase = n_blk * BN + half * SLICE;
+          l_ok = kb1 > kb0 && l_m0 < (int)gp.ep[l_p].M;
+        }
+        if (l_ok && l_nbase + lg * GW < (int)gp.ep[l_p].N) return;
+      }
+    };
+    auto issue_load = [&]() {                            // (warp-uniform bookkeeping; lane 0 talks to the TMA unit)
+      if (!l_valid) return;
+      const int b = issued % NBOX;
+      if (lane == 0) {
+        mbar_expect_tx(aux_bar(ew, b), kTmaBox);
+        tma_load_2d(boxes + (uint32_t)b * kTmaBox, &gp.taux[l_p], aux_bar(ew, b), l_nbase + lg * GW, l_m0);
+      }
+      ++issued;
+      lc_advance();
+    };
+    lc_advance();
+    for (int i = 0; i < NBOX - 1; ++i) issue_load();      // boxes in flight before the first accumulator is ready
+    int local = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int p, tl, m_blk, n_blk, sp, kb0, kb1;
+      locate(t, p, tl);
+      gp.ts[p].decode(tl, m_blk, n_blk, sp, kb0, kb1);
+      if (kb1 <= kb0) continue;
+      const EpiParams& ep = gp.ep[p];
+      const CUtensorMap* tmap_c = &gp.tc[p];
+      const int acc = local % NACC;
+      const uint32_t acc_phase = (local / NACC) & 1u;
+      ++local;
+      const int m0 = m_blk * (BM * CG) + (int)cta_rank * BM + quad * 32;     // first row of this warp's boxes
+      const int n_base = n_blk * BN + half * SLICE;
+      const bool live = m0 < (int)ep.M;
+      const bool add_bias = kBias && sp == 0 && ep.bias != nullptr;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * SLICE);
+#pragma unroll 1
+      for (int g = 0; g < NGRP; ++g) {
+        uint32_t z[GW / 32][32];
+#pragma unroll
+        for (int h = 0; h < GW / 32; ++h) tmem_ld_32x32b_x32_issue(trow + g * GW + h * 32, z[h]);
+        const int n0 = n_base + g * GW;
+        const bool active = live && n0 < (int)ep.N;   // warp-uniform; the same predicate drives the load cursor
+        const uint32_t box = boxes + (uint32_t)(done % NBOX) * kTmaBox;
+        if (active) mbar_wait(aux_bar(ew, done % NBOX), (uint32_t)(done / NBOX) & 1u);       // the operand of this group has landed
+#pragma unroll
+        for (int h = 0; h < GW / 32; ++h) tmem_ld_wait(z[h]);
+        if (g == NGRP - 1) {                          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2 && !lead_cta) mbar_arrive_remote(tempty_bar(acc), 0);
+            else mbar_arrive(tempty_bar(acc));
+          }
+        }
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {               // one 16-byte piece of the row segment: 8 bf16 or 4 f32 columns, in place
+            const uint32_t pos = box + my_row + (((uint32_t)j ^ sw) << 4);
+            const uint4 u = lds_128(pos);
+            if constexpr (kF32) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(z[0][j * 4 + e]);
+              if (add_bias && n0 + j * 4 < (int)ep.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j * 4));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              sts_128(pos, __float_as_uint(v[0] + __uint_as_float(u.x)), __float_as_uint(v[1] + __uint_as_float(u.y)),
+                      __float_as_uint(v[2] + __uint_as_float(u.z)), __float_as_uint(v[3] + __uint_as_float(u.w)));
+            } else {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(z[j >> 2][(j & 3) * 8 + e]);
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              sts_128(pos, pack_bf16x2(v[0] * a0.x, v[1] * a0.y), pack_bf16x2(v[2] * a1.x, v[3] * a1.y),
+                      pack_bf16x2(v[4] * a2.x, v[5] * a2.y), pack_bf16x2(v[6] * a3.x, v[7] * a3.y));
+            }
+          }
+          fence_async_smem();                          // generic-proxy writes -> visible to the TMA engine
+        }
+        __syncwarp();
+        if (active) {
+          if (lane == 0) {
+            tma_store_2d(tmap_c, box, n0, m0);
+            bulk_commit();
+            bulk_wait_read<1>();                       // every store but this one has read its box: the box of the previous group is free
+          }
+          ++done;
+          issue_load();                                // operand of the group after next, into the box just freed
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();                // the boxes must outlive the stores that read them
+    __syncwarp();
   } else if constexpr (direct_epi(EPI)) {
     // ===================== TMA epilogue (every compile-time epilogue) =====================
     // tcgen05.ld hands every lane consecutive columns of ITS row.  The lane applies the epilogue in registers and
@@ -356,8 +491,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
       const bool live = m0 < (int)ep.M;                // a box entirely below the matrix is neither loaded nor stored
       const bool add_bias = kBias && sp == 0 && ep.bias != nullptr;
       if (kLoad && live && lane == 0 && n_base < (int)ep.N) {     // operand box of group 0: in flight while the MMAs of this tile still run
-        mbar_expect_tx(aux_bar(ew), kTmaBox);
-        tma_load_2d(box1, tmap_x, aux_bar(ew), n_base, m0);
+        mbar_expect_tx(aux_bar(ew, 0), kTmaBox);
+        tma_load_2d(box1, tmap_x, aux_bar(ew, 0), n_base, m0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -388,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
         }
         const bool active = live && n0 < (int)ep.N;   // warp-uniform
         if (active) {
-          if (kLoad) { mbar_wait(aux_bar(ew), aux_phase); aux_phase ^= 1u; }
+          if (kLoad) { mbar_wait(aux_bar(ew, 0), aux_phase); aux_phase ^= 1u; }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {               // one 16-byte piece of the row segment: 8 bf16 or 4 f32 columns
             const uint32_t pos = my_row + (((uint32_t)j ^ sw) << 4);
@@ -437,8 +572,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup<NG> gp) {
           }
           bulk_commit();
           if (kLoad && live && g + 1 < NGRP && n0 + GW < (int)ep.N) {     // next group's operand box
-            mbar_expect_tx(aux_bar(ew), kTmaBox);
-            tma_load_2d(box1, tmap_x, aux_bar(ew), n0 + GW, m0);
+            mbar_expect_tx(aux_bar(ew, 0), kTmaBox);
+            tma_load_2d(box1, tmap_x, aux_bar(ew, 0), n0 + GW, m0);
           }
         }
       }
@@ -672,7 +807,7 @@ static int launch_group_ew(const GemmGroup<NG>& gp, cudaStream_t st) {
   constexpr int STAGES = fit_stages(STAGES_, EPI, EW, BN, CG);
   static_assert(STAGES >= 3, "pipeline too shallow");
   constexpr int kNumThreads = 64 + 32 * EW;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EPI, EW) + ones_bytes(EPI) + 8 * (2 * STAGES + 5 + EW) + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + staging_bytes(EPI, EW, BN, CG) + ones_bytes(EPI) + 8 * (2 * STAGES + 5 + 3 * EW) + 16 + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory of an SM");
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, STAGES, AK, BKM, EPI, CG, EW, NG>;

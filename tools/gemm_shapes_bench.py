@@ -9,8 +9,9 @@ import deepavfusion_b200.kernels as K
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-trainer = bench.build_trainer(dev, False)
-img, aud = bench.synth_inputs(bench.BATCH_PER_GPU, 1000, False)
+CFG = bench.CONFIGS[os.environ.get("DAVF_BENCH_CONFIG", "vggsound")]
+trainer = bench.build_trainer(CFG, dev, False)
+img, aud = bench.synth_inputs(CFG, CFG["batch"], 1000, False)[:2]
 img, aud = img.to(dev), aud.to(dev)
 K.GEMM_TRACE = []
 li, la, _, _ = trainer.model(img, aud)
