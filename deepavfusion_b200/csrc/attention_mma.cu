@@ -415,7 +415,11 @@ static int launch_fwd_nw(const davf_attn_fwd_args& a, cudaStream_t st) {
 }
 template <int DQK, int DV>
 static int launch_fwd(const davf_attn_fwd_args& a, cudaStream_t st) {
-  if (a.Nq <= 16) return launch_fwd_nw<DQK, DV, 1>(a, st);      // fusion-token attentions: 8 / 16 queries
+  // fusion-token attentions (8 / 16 queries): one or two warps compute; with >= 32 keys FOUR warps stage the head's K / V into
+  // shared memory (the extra warps leave after the load: with one warp the 12 KB of a 49-key head were 25 dependent 16-byte
+  // loads per lane; measured 14.0 -> 10.9 us at 49 keys, while at 19 keys the wider CTA loses: 7.6 -> 8.7 us)
+  if (a.Nq <= 32 && a.Nk >= 32) return launch_fwd_nw<DQK, DV, 4>(a, st);
+  if (a.Nq <= 16) return launch_fwd_nw<DQK, DV, 1>(a, st);
   if (a.Nq <= 32) return launch_fwd_nw<DQK, DV, 2>(a, st);
   // long sequences (decoders: 228 / 128 queries): more query rows per CTA, so the head's K / V tile is staged
   // into shared memory by fewer CTAs (DAVF_ATTN_FWD_NW = 4 / 8 / 16 overrides, for experiments)

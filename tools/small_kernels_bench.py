@@ -84,6 +84,7 @@ if __name__ == "__main__":
         attn(32, 12, 228, 32, 64, "enc image full")
         attn(32, 12, 128, 32, 64, "enc audio full")
         attn(64, 12, 49, 41, 64, "cross v (8q)")
+        attn(64, 12, 19, 11, 64, "cross a (8q)")
     K.set_attn_impl(0)
     ln(64, 32, 49, 768, "enc image")
     ln(64, 49, 0, 768, "enc image mlp")
