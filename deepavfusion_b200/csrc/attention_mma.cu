@@ -455,7 +455,7 @@ static int launch_bwd(const davf_attn_bwd_args& a, cudaStream_t st) {
   return launch_bwd_nw<DQK, DV, 8>(a, st);
 }
 
-// tcgen05 / TMEM / TMA kernels (attention_tc.cu): every problem with more than 16 query rows and head dim 64 / 32
+// tcgen05 / TMEM / TMA kernels (attention_tc.cu): every problem with at least 8 query rows and head dim 64 / 32
 bool attn_tc_fwd_ok(const davf_attn_fwd_args& a);
 bool attn_tc_bwd_ok(const davf_attn_bwd_args& a);
 int attn_tc_fwd(const davf_attn_fwd_args& a, cudaStream_t st);

@@ -1,7 +1,7 @@
 // K6/K8: fused self-attention on the 5th-generation tensor cores, forward and backward.
 //
-// Replaces timm Attention's SDPA call (vits.py:32-34, avmae.py:53-55,83-85) for every (batch, head) problem with more
-// than 16 query rows: the modality encoder blocks (49 / 19 live queries against 81 / 51 keys, or 196 / 96 against
+// Replaces timm Attention's SDPA call (vits.py:32-34, avmae.py:53-55,83-85) and the fusion block's CrossAttention
+// (fusion_blocks.py:46-59) for every (batch, head) problem with at least 8 query rows and head dim 64 / 32: the modality encoder blocks (49 / 19 live queries against 81 / 51 keys, or 196 / 96 against
 // 228 / 128 unmasked; head dim 64) and the MAE decoders (228 / 128 tokens, head dim 32).
 //
 // Data flow (no score matrix, no transposed copy ever touches HBM):
@@ -685,7 +685,9 @@ static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool m8(int64_t x) { return x % 8 == 0; }
 
 static int attn_tc_min_q() {
-  static const int v = [] { const char* e = getenv("DAVF_ATTN_TC_MINQ"); return e ? atoi(e) : 17; }();
+  // 8: the fusion block's 8-query cross attentions too (backward 29.8 -> 20.2 us at 49 keys, step 16.29 -> 16.08 ms); below that
+  // (and for the dqk = 16 pair attention) the mma.sync kernels serve
+  static const int v = [] { const char* e = getenv("DAVF_ATTN_TC_MINQ"); return e ? atoi(e) : 8; }();
   return v;
 }
 

@@ -41,7 +41,7 @@ int davf_device_sm(void);                     /* 100 for B200, <0 on error      
 /* 1 (default): large launches use the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles);
  * 0: single-CTA kernel only (A/B comparison in tests and benches). */
 int davf_set_gemm_2cta(int on);
-/* 0 = default: tcgen05 / TMEM / TMA attention for problems with more than 16 query rows and head dim 64 / 32, warp-level
+/* 0 = default: tcgen05 / TMEM / TMA attention for problems with at least 8 query rows and head dim 64 / 32, warp-level
  * mma.sync attention for the tiny fusion-token problems; 2 = mma.sync attention for every problem (A/B comparison in
  * tests and benches).  (The CUDA-core checker kernels the tests compare against live in tests/check/libdavf_check.so.) */
 int davf_set_attn_impl(int impl);

@@ -289,7 +289,7 @@ def test_gemm_all_modes(impl, streamk):
                                                    (3, 3, 17, 17, 32, 32, 0), (2, 4, 256, 256, 64, 64, 0), (5, 2, 130, 20, 32, 32, 0)])
 @pytest.mark.parametrize("impl", [0, 2, 1], ids=["tcgen05", "mma", "simt"])
 def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
-    """impl 0 = product dispatch: tcgen05 / TMEM / TMA kernels for > 16 query rows at head dim 64 / 32 (asserted through the
+    """impl 0 = product dispatch: tcgen05 / TMEM / TMA kernels for >= 8 query rows at head dim 64 / 32 (asserted through the
     per-family launch counter), mma.sync kernels for the tiny fusion-token problems; 2 = mma.sync everywhere; 1 = the CUDA-core
     checker kernels of tests/check/libdavf_check.so behind the same wrappers (checks the checker against the torch emulation)."""
     if impl == 1 and B * H * Nq * Nk > 3_000_000:
@@ -302,7 +302,7 @@ def test_attention_fwd_bwd(K, B, H, Nq, Nk, dqk, dv, skip, impl):
         with ctx:
             _attention_case(K, B, H, Nq, Nk, dqk, dv, skip)
         tc = K.launch_count_kind(K.KIND_ATTN_TC) - n0
-        eligible = impl == 0 and Nq > 16 and dqk == dv and dqk in (32, 64)
+        eligible = impl == 0 and Nq >= 8 and dqk == dv and dqk in (32, 64)
         packed = dqk == dv and Nq + skip <= Nk and skip > 0
         assert tc == ((3 if packed else 2) if eligible else 0), tc    # forward + the one-pass backward(s); the two-pass backward has no forward output
     finally:

@@ -5,7 +5,7 @@ mathematically-zero K-bias gradients, global rel-L2 <= 2e-2; losses rtol 2e-3; p
 
 The tiny-dimension tests never reach the kernels the benchmark runs on: the CTA-pair GEMM
 (``gemm_tc_kernel<256, ..., CG = 2>``) needs M, N >= 256 with >= 36 pair tiles, the tcgen05 attention needs
->= 17 query rows.  Each case below therefore also asserts, through ``davf_launch_count_kind``, that those kernel
+>= 8 query rows.  Each case below therefore also asserts, through ``davf_launch_count_kind``, that those kernel
 families were the ones that served it.
 
   vggsound_b64   BASELINE configs[1]: r = 0.25 / mlp 1, 64 pairs (the bench workload)   avmae.py:216-236
