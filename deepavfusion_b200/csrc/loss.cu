@@ -13,7 +13,11 @@ struct PatchGeom { int B, C, H, W, p, gW, L, P; };
 
 // loads the patch of (b,l) into registers in MEMORY order (c, py, px) and returns per-lane
 // normalised targets together with the index e = (py*p + px)*C + c of each in the pred row.
-template <bool BWD>
+// PS = log2(patch size) when it is a compile-time power of two (16 x 16 patches everywhere on the path: the index
+// arithmetic is shifts; with run-time divisors the kernel was bound by ~150 integer divisions per lane and patch),
+// 0 = generic.  The prediction row is fetched together with the pixels (one latency phase, not two), and the backward's
+// dpred row is transposed through shared memory into 16-byte stores (it was 768 two-byte stores at a 6-byte stride).
+template <bool BWD, int PS>
 __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict__ img, const float* __restrict__ pred,
                                                          const float* __restrict__ mask, float* __restrict__ loss_sum,
                                                          const float* __restrict__ gscale, float inv_count,
@@ -22,9 +26,11 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[8];
+  __shared__ __align__(16) uint16_t stg[BWD ? 8 : 1][BWD ? 32 * kMaxPerLane : 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t patch = (int64_t)blockIdx.x * 8 + warp;
   const int64_t npatch = (int64_t)g.B * g.L;
+  const bool vec_rows = (g.P & 7) == 0;                 // dpred rows are 16-byte multiples
   float lsum = 0.f;
   if (patch < npatch) {
     const int b = (int)(patch / g.L), l = (int)(patch - (int64_t)b * g.L);
@@ -32,21 +38,28 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
     if (!masked) {
       if (BWD) {
         uint16_t* dr = dpred + patch * g.P;
-        for (int e = lane * 2; e < g.P; e += 64) *reinterpret_cast<uint32_t*>(dr + e) = 0u;
+        if (vec_rows) { for (int e = lane * 8; e < g.P; e += 256) *reinterpret_cast<uint4*>(dr + e) = make_uint4(0u, 0u, 0u, 0u); }
+        else { for (int e = lane * 2; e < g.P; e += 64) *reinterpret_cast<uint32_t*>(dr + e) = 0u; }
       }
     } else {
       const int gy = l / g.gW, gx = l - gy * g.gW;
       const float* prow = pred + ((int64_t)b * pred_G + pred_off + l) * g.P;
-      float x[kMaxPerLane];
-      float s = 0.f;
       const int pp = g.p * g.p;
+      auto split = [&](int idx, int& c, int& r, int& py, int& px) {
+        if (PS > 0) { c = idx >> (2 * PS); r = idx & ((1 << (2 * PS)) - 1); py = r >> PS; px = r & ((1 << PS) - 1); }
+        else { c = idx / pp; r = idx - c * pp; py = r / g.p; px = r - py * g.p; }
+      };
+      float x[kMaxPerLane], pr[kMaxPerLane];
+      float s = 0.f;
 #pragma unroll
       for (int t = 0; t < kMaxPerLane; ++t) {
         const int idx = lane + 32 * t;
-        x[t] = 0.f;
+        x[t] = 0.f; pr[t] = 0.f;
         if (idx < g.P) {
-          const int c = idx / pp, r = idx - c * pp, py = r / g.p, px = r - py * g.p;
+          int c, r, py, px;
+          split(idx, c, r, py, px);
           x[t] = img[(((int64_t)b * g.C + c) * g.H + gy * g.p + py) * g.W + gx * g.p + px];
+          pr[t] = prow[r * g.C + c];                               // (py, px, c) order of patchify
           s += x[t];
         }
       }
@@ -65,12 +78,18 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
       for (int t = 0; t < kMaxPerLane; ++t) {
         const int idx = lane + 32 * t;
         if (idx < g.P) {
-          const int c = idx / pp, r = idx - c * pp;
-          const int e = r * g.C + c;                               // (py, px, c) order of patchify
-          const float diff = prow[e] - (x[t] - mean) * rs;
-          if (BWD) dpred[patch * g.P + e] = f32_to_bf16(gs * diff);
+          int c, r, py, px;
+          split(idx, c, r, py, px);
+          const float diff = pr[t] - (x[t] - mean) * rs;
+          if (BWD) stg[warp][r * g.C + c] = f32_to_bf16(gs * diff);
           else lsum += diff * diff;
         }
+      }
+      if (BWD) {
+        __syncwarp();
+        uint16_t* dr = dpred + patch * g.P;
+        if (vec_rows) { for (int e = lane * 8; e < g.P; e += 256) *reinterpret_cast<uint4*>(dr + e) = *reinterpret_cast<const uint4*>(&stg[warp][e]); }
+        else { for (int e = lane * 2; e < g.P; e += 64) *reinterpret_cast<uint32_t*>(dr + e) = *reinterpret_cast<const uint32_t*>(&stg[warp][e]); }
       }
       lsum = warp_sum(lsum) / (float)g.P;
     }
@@ -104,7 +123,8 @@ extern "C" int davf_masked_mse_fwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(geom(g, B, C, H, W, p) == 0, "masked_mse_fwd: unsupported geometry C=%d H=%d W=%d p=%d", C, H, W, p);
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  DAVF_CUDA(launch_pdl(masked_mse_kernel<false>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
+  if (p == 16) DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 4>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
+  else DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 0>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -117,7 +137,8 @@ extern "C" int davf_masked_mse_bwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(gscale && dpred, "masked_mse_bwd: null pointer");
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  DAVF_CUDA(launch_pdl(masked_mse_kernel<true>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
+  if (p == 16) DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 4>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
+  else DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 0>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
