@@ -15,9 +15,12 @@ struct PatchGeom { int B, C, H, W, p, gW, L, P; };
 // normalised targets together with the index e = (py*p + px)*C + c of each in the pred row.
 // PS = log2(patch size) when it is a compile-time power of two (16 x 16 patches everywhere on the path: the index
 // arithmetic is shifts; with run-time divisors the kernel was bound by ~150 integer divisions per lane and patch),
-// 0 = generic.  The prediction row is fetched together with the pixels (one latency phase, not two), and the backward's
+// 0 = generic; NT = P / 32 elements per lane when known at compile time (24: 16 x 16 x 3 frames, 8: spectrogram patches; 0 =
+// generic, up to 32 with bounds checks).  ALL loads of a patch -- pixels and prediction row -- are issued unconditionally
+// before the first use (ncu: with the loads inside `if (idx < P)` blocks next to their accumulation every load's latency was
+// paid in turn, 92 us for 58 MB), and the backward's
 // dpred row is transposed through shared memory into 16-byte stores (it was 768 two-byte stores at a 6-byte stride).
-template <bool BWD, int PS>
+template <bool BWD, int PS, int NT>
 __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict__ img, const float* __restrict__ pred,
                                                          const float* __restrict__ mask, float* __restrict__ loss_sum,
                                                          const float* __restrict__ gscale, float inv_count,
@@ -49,35 +52,38 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
         if (PS > 0) { c = idx >> (2 * PS); r = idx & ((1 << (2 * PS)) - 1); py = r >> PS; px = r & ((1 << PS) - 1); }
         else { c = idx / pp; r = idx - c * pp; py = r / g.p; px = r - py * g.p; }
       };
-      float x[kMaxPerLane], pr[kMaxPerLane];
+      constexpr int TN = NT > 0 ? NT : kMaxPerLane;
+      float x[TN], pr[TN];
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {                     // every load in flight before anything is consumed
+        const int idx = lane + 32 * t;
+        const bool ok = NT > 0 || idx < g.P;
+        int c, r, py, px;
+        split(ok ? idx : 0, c, r, py, px);
+        x[t] = __ldg(img + (((int64_t)b * g.C + c) * g.H + gy * g.p + py) * g.W + gx * g.p + px);
+        pr[t] = __ldg(prow + r * g.C + c);               // (py, px, c) order of patchify
+      }
       float s = 0.f;
 #pragma unroll
-      for (int t = 0; t < kMaxPerLane; ++t) {
-        const int idx = lane + 32 * t;
-        x[t] = 0.f; pr[t] = 0.f;
-        if (idx < g.P) {
-          int c, r, py, px;
-          split(idx, c, r, py, px);
-          x[t] = img[(((int64_t)b * g.C + c) * g.H + gy * g.p + py) * g.W + gx * g.p + px];
-          pr[t] = prow[r * g.C + c];                               // (py, px, c) order of patchify
-          s += x[t];
-        }
+      for (int t = 0; t < TN; ++t) {
+        if (NT == 0 && lane + 32 * t >= g.P) { x[t] = 0.f; pr[t] = 0.f; }
+        s += x[t];
       }
       float mean = 0.f, rs = 1.f;
       if (norm_pix) {
         mean = warp_sum(s) / (float)g.P;
         float sq = 0.f;
 #pragma unroll
-        for (int t = 0; t < kMaxPerLane; ++t)
-          if (lane + 32 * t < g.P) { const float d = x[t] - mean; sq += d * d; }
+        for (int t = 0; t < TN; ++t)
+          if (NT > 0 || lane + 32 * t < g.P) { const float d = x[t] - mean; sq += d * d; }
         const float var = warp_sum(sq) / (float)(g.P - 1);          // unbiased, avmae.py:191
         rs = rsqrtf(var + 1.0e-6f);
       }
       const float gs = BWD ? gscale[0] * inv_count * 2.0f / (float)g.P : 0.f;
 #pragma unroll
-      for (int t = 0; t < kMaxPerLane; ++t) {
+      for (int t = 0; t < TN; ++t) {
         const int idx = lane + 32 * t;
-        if (idx < g.P) {
+        if (NT > 0 || idx < g.P) {
           int c, r, py, px;
           split(idx, c, r, py, px);
           const float diff = pr[t] - (x[t] - mean) * rs;
@@ -123,8 +129,10 @@ extern "C" int davf_masked_mse_fwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(geom(g, B, C, H, W, p) == 0, "masked_mse_fwd: unsupported geometry C=%d H=%d W=%d p=%d", C, H, W, p);
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  if (p == 16) DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 4>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
-  else DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 0>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
+  const dim3 grid((int)((np + 7) / 8));
+  if (p == 16 && g.P == 768) DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 4, 24>, grid, dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
+  else if (p == 16 && g.P == 256) DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 4, 8>, grid, dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
+  else DAVF_CUDA(launch_pdl(masked_mse_kernel<false, 0, 0>, grid, dim3(256), 0, as_stream(s), img, pred, mask, loss_sum, nullptr, 0.f, nullptr, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
@@ -137,8 +145,10 @@ extern "C" int davf_masked_mse_bwd(const float* img, const float* pred, const fl
   DAVF_CHECK_ARG(gscale && dpred, "masked_mse_bwd: null pointer");
   if (B == 0) return DAVF_OK;
   const int64_t np = (int64_t)B * g.L;
-  if (p == 16) DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 4>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
-  else DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 0>, dim3((int)((np + 7) / 8)), dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
+  const dim3 grid((int)((np + 7) / 8));
+  if (p == 16 && g.P == 768) DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 4, 24>, grid, dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
+  else if (p == 16 && g.P == 256) DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 4, 8>, grid, dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
+  else DAVF_CUDA(launch_pdl(masked_mse_kernel<true, 0, 0>, grid, dim3(256), 0, as_stream(s), img, pred, mask, nullptr, gscale, inv_count, dpred, g, pred_G, pred_off, norm_pix));
   DAVF_LAUNCH_OK();
   return DAVF_OK;
 }
