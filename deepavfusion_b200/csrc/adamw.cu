@@ -5,6 +5,7 @@
 // Per-parameter-group hyper-parameters come from device tables (a group id per 64-element chunk
 // and {lr, weight_decay} per group) so LR schedules never re-capture a CUDA graph and arbitrary
 // groupings (weight-decay split, "pretrained" groups, layer-wise lr decay) cost nothing.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace davf {
@@ -82,8 +83,12 @@ extern "C" int davf_adamw_step(float* p, float* g, float* m, float* v, davf_bf16
   DAVF_CHECK_ARG(p && g && m && v && hp && scal && chunk_group, "adamw_step: null pointer");
   DAVF_CHECK_ARG(n % kChunk == 0, "adamw_step: n=%lld must be a multiple of %d", (long long)n, kChunk);
   if (n == 0) return DAVF_OK;
+  // Every CTA resident at once and half of each SM's thread slots left free: a bucket's AdamW runs beside the NEXT bucket's
+  // NCCL all-reduce and the backward GEMMs.  With 16 CTAs per SM (two waves of eight) the block scheduler drained AdamW's
+  // queue before it dispatched a single NCCL CTA, which put all-reduce and AdamW in series at the end of the step.
+  static const int per_sm = [] { const char* e = getenv("DAVF_ADAMW_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 4096 ? 4096 : v); }();
   int64_t blocks = (n / 4 + 255) / 256;
-  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks > (int64_t)per_sm * kNumSMs) blocks = (int64_t)per_sm * kNumSMs;
   DAVF_CUDA(launch_pdl(adamw_kernel, dim3((int)blocks), dim3(256), 0, as_stream(s), reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
                                                      reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p_bf16), n / 4, chunk_group, hp,
                                                      scal, beta1, beta2, eps, zero_grad, sumsq_out));

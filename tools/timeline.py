@@ -6,10 +6,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from deepavfusion_b200.util.graphed import GraphedTrainStep
-dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+WORLD, RANK = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))     # under torchrun: every rank steps, rank 0 profiles
+LOCAL = 0
+if WORLD > 1:
+    from deepavfusion_b200.util import distributed as dist_utils
+    LOCAL = dist_utils.init_from_env("nccl")
+dev = torch.device("cuda", LOCAL); torch.cuda.set_device(LOCAL)
 CFG = bench.CONFIGS[os.environ.get("DAVF_BENCH_CONFIG", "vggsound")]
-trainer = bench.build_trainer(CFG, dev, False)
-img, aud = bench.synth_inputs(CFG, CFG["batch"], 1000, False)[:2]
+trainer = bench.build_trainer(CFG, dev, WORLD > 1)
+img, aud = bench.synth_inputs(CFG, CFG["batch"], 1000 + RANK, False)[:2]
 img, aud = img.to(dev), aud.to(dev)
 def _eager():
     li, la, _, _ = trainer.model(img, aud); trainer.step(li + la)
@@ -19,10 +24,14 @@ for _ in range(3): g(img, aud)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 NSTEPS = int(os.environ.get("DAVF_TIMELINE_STEPS", "1"))      # > 1: back-to-back replays, the host running ahead as in training
+if RANK != 0:
+    for _ in range(NSTEPS): g(img, aud)
+    torch.cuda.synchronize(); torch.distributed.barrier(); sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(NSTEPS):
         g(img, aud)
     torch.cuda.synchronize()
+if WORLD > 1: torch.distributed.barrier()
 os.makedirs("gpurun_out", exist_ok=True)
 prof.export_chrome_trace("gpurun_out/timeline.json")
 ev = json.load(open("gpurun_out/timeline.json"))["traceEvents"]
@@ -67,5 +76,16 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:24]: out.append(f"{v / 1
 out.append("first 40 kernels (start ms, dur us, stream, name):")
 for e in ks[:40]: out.append(f"  {(e['ts'] - t0) / 1e3:7.3f} {e['dur']:7.1f} {e['args'].get('stream')} {e['name'][:70]}")
 out.append(f"sum of kernel time {sum(e['dur'] for e in ks) / 1e3:.2f} ms")
-open("gpurun_out/timeline_summary.txt", "w").write("\n".join(out))
+if WORLD > 1:
+    # the exchange step: every NCCL kernel and the AdamW launch that follows it, against the end of backward
+    out.append("exchange step (start ms, dur us, name):")
+    for e in ks:
+        if "nccl" in e["name"].lower() or "adamw" in e["name"]:
+            out.append(f"  {(e['ts'] - t0) / 1e3:7.3f} {e['dur']:8.1f} {e['name'][:60]}")
+    nc = [e for e in ks if "nccl" in e["name"].lower()]
+    other = [e for e in ks if "nccl" not in e["name"].lower() and "adamw" not in e["name"]]
+    out.append(f"NCCL busy {sum(e['dur'] for e in nc) / 1e3:.2f} ms over {len(nc)} kernels; last compute kernel ends at "
+               f"{max(e['ts'] + e['dur'] for e in other) / 1e3 - t0 / 1e3:.2f} ms, step ends at {(t1 - t0) / 1e3:.2f} ms")
+SUFFIX = os.environ.get("DAVF_TIMELINE_TAG", "")
+open(f"gpurun_out/timeline_summary{SUFFIX}.txt", "w").write("\n".join(out))
 print("\n".join(out))
