@@ -672,6 +672,8 @@ def run_ours(args):
         if rank == 0:
             dp["nccl"] = nccl_summary()
             dp["gemm_sms_backward"] = 148 - int(os.environ.get("DAVF_COMM_SMS", "32"))      # forward launches use all 148
+            dp["grad_buffer_nccl_registered"] = trainer.grad_buffer_registered               # True, or why not
+            dp["nccl_high_priority_stream"] = os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "1") != "0"
 
     # ---- roofline of the dominant kernel + baselines (rank 0) -----------------------------------------
     roof, base, eager = None, None, None

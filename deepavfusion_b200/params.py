@@ -218,6 +218,19 @@ class ParamStore:
                     self._g[k].copy_(p.grad)
                 p.grad = self._g[k]
 
+    def rehome_grads(self, buf: torch.Tensor) -> None:
+        """Moves ``flat_g`` into ``buf`` (same size / dtype / device; e.g. memory registered with the NCCL communicator,
+        util.distributed.nccl_registered_zeros) and re-points every gradient view at it."""
+        assert buf.shape == self.flat_g.shape and buf.dtype == self.flat_g.dtype and buf.device == self.flat_g.device
+        with torch.no_grad():
+            buf.copy_(self.flat_g)
+            self.flat_g = buf
+            self._g = [buf[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+            for k, p in enumerate(self.params):
+                if p.requires_grad:
+                    p.grad = self._g[k]
+        self._lowp_grads.clear()
+
     def grad(self, p: nn.Parameter) -> torch.Tensor:
         k = self._index[id(p)]
         if not self._attached(p, k):

@@ -48,8 +48,32 @@ def init_from_env(backend: Optional[str] = None) -> int:
         kw = {}
         if backend == "nccl":
             kw["device_id"] = torch.device("cuda", local)
+            if os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "1") != "0":
+                # at N = 8 the bucket all-reduce chain is the critical path of backward: its CTAs go ahead of queued compute CTAs
+                kw["pg_options"] = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group(backend=backend, **kw)
     return local
+
+
+def nccl_registered_zeros(numel: int, device, group=None):
+    """An f32 buffer from NCCL's own allocator (``ncclMemAlloc``), registered with the communicator, so that NVLS
+    all-reduces work on it in place (multimem load-reduce / store straight on the user buffer) instead of staging
+    every bucket through NCCL's internal buffers.  Returns ``(tensor, pool)`` -- keep the pool alive as long as the
+    tensor -- or ``(None, reason)`` when the process group is not NCCL or registration is unavailable."""
+    if os.environ.get("DAVF_NCCL_REGISTER", "1") == "0":
+        return None, "disabled by DAVF_NCCL_REGISTER=0"
+    if not (is_dist_avail_and_initialized() and dist.get_backend(group) == "nccl"):
+        return None, "process group is not NCCL"
+    try:
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        backend = pg._get_backend(torch.device(device))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool, device=torch.device(device)):
+            buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        backend.register_mem_pool(pool)
+        return buf, pool
+    except Exception as e:      # noqa: BLE001 -- an unregistered buffer is slower, not wrong; the reason is reported by bench.py
+        return None, f"{type(e).__name__}: {e}"
 
 
 class GradSync:

@@ -50,7 +50,16 @@ class Trainer:
         overlap_opt = isinstance(self.optimizer, FusedAdamW) and mode != "0" and (self.store.flat_g.is_cuda or mode == "force")
         self.sync = dist_utils.GradSync(self.store, bucket_mb=bucket_mb, optimizer=self.optimizer if overlap_opt else None) \
             if (self.distributed or overlap_opt) else None
+        self.grad_buffer_registered = "single process"
         if self.distributed:
+            if self.store.flat_g.is_cuda:
+                # the gradient buffer lives in NCCL-registered memory: NVLS all-reduces run in place on it
+                buf, pool = dist_utils.nccl_registered_zeros(self.store.numel, self.store.device)
+                if buf is not None:
+                    self.store.rehome_grads(buf)
+                    self._nccl_pool, self.grad_buffer_registered = pool, True
+                else:
+                    self.grad_buffer_registered = pool          # the reason
             self.broadcast_parameters()
             # SMs left to the NCCL kernels that run under backward (see davf_set_gemm_sms).  Only BACKWARD launches of the
             # final micro-step overlap the bucket all-reduces: forward (and accumulate-only) launches keep the whole machine.
