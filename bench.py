@@ -463,6 +463,11 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        # a multi-rank run that stops making progress (a collective some rank never joins) must end on its own with the
+        # Python stacks on stderr instead of sitting there until the caller's limit: a normal run takes under a minute
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("DAVF_BENCH_WATCHDOG_S", "600")), exit=True)
     local = dist_utils.init_from_env("nccl") if world > 1 else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -673,7 +678,7 @@ def run_ours(args):
             dp["nccl"] = nccl_summary()
             dp["gemm_sms_backward"] = 148 - int(os.environ.get("DAVF_COMM_SMS", "32"))      # forward launches use all 148
             dp["grad_buffer_nccl_registered"] = trainer.grad_buffer_registered               # True, or why not
-            dp["nccl_high_priority_stream"] = os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "1") != "0"
+            dp["nccl_high_priority_stream"] = os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "0") == "1"
 
     # ---- roofline of the dominant kernel + baselines (rank 0) -----------------------------------------
     roof, base, eager = None, None, None

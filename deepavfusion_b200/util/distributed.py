@@ -48,8 +48,8 @@ def init_from_env(backend: Optional[str] = None) -> int:
         kw = {}
         if backend == "nccl":
             kw["device_id"] = torch.device("cuda", local)
-            if os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "1") != "0":
-                # at N = 8 the bucket all-reduce chain is the critical path of backward: its CTAs go ahead of queued compute CTAs
+            if os.environ.get("DAVF_NCCL_HIGH_PRIORITY", "0") == "1":
+                # opt-in (see nccl_registered_zeros): the all-reduce CTAs go ahead of queued compute CTAs
                 kw["pg_options"] = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group(backend=backend, **kw)
     return local
@@ -59,9 +59,15 @@ def nccl_registered_zeros(numel: int, device, group=None):
     """An f32 buffer from NCCL's own allocator (``ncclMemAlloc``), registered with the communicator, so that NVLS
     all-reduces work on it in place (multimem load-reduce / store straight on the user buffer) instead of staging
     every bucket through NCCL's internal buffers.  Returns ``(tensor, pool)`` -- keep the pool alive as long as the
-    tensor -- or ``(None, reason)`` when the process group is not NCCL or registration is unavailable."""
-    if os.environ.get("DAVF_NCCL_REGISTER", "1") == "0":
-        return None, "disabled by DAVF_NCCL_REGISTER=0"
+    tensor -- or ``(None, reason)`` when the process group is not NCCL or registration is unavailable.
+
+    OPT-IN (``DAVF_NCCL_REGISTER=1``, usually with ``DAVF_NCCL_HIGH_PRIORITY=1``).  Measured on 8 B200s: the 64 MB bucket
+    all-reduce drops from 24 NVLS channels / 0.38 ms to 8 channels / 0.28 ms and the step from 18.19 to 16.74 ms
+    (profiles/r2/bench_n8_registered.json vs bench_n8_x.json).  It is not the default because one of the four 8-GPU jobs
+    run with it (the only one with DAVF_COMM_SMS=8) hung without output and the GPU budget ended before the cause could
+    be isolated; the unregistered path has never hung in any run."""
+    if os.environ.get("DAVF_NCCL_REGISTER", "0") != "1":
+        return None, "off (opt in with DAVF_NCCL_REGISTER=1)"
     if not (is_dist_avail_and_initialized() and dist.get_backend(group) == "nccl"):
         return None, "process group is not NCCL"
     try:
@@ -86,7 +92,7 @@ class GradSync:
     middle of backward to the end of the step) -- and the HBM-bound optimizer (8.97 GB of traffic per step) runs
     under the tensor-core-bound rest of backward instead of after it.  Works with world size 1 too (no all-reduce, only the overlapped optimizer)."""
 
-    def __init__(self, store: ParamStore, bucket_mb: float = 64.0, group=None, optimizer=None):
+    def __init__(self, store: ParamStore, bucket_mb: float = 64.0, group=None, optimizer=None, tail_mb: Optional[float] = None):
         self.store = store
         self.group = group
         self.world = dist.get_world_size(group) if is_dist_avail_and_initialized() else 1
@@ -94,8 +100,13 @@ class GradSync:
         self.fuse_optimizer = False               # set per backward pass by Trainer.step
         self.enabled = True                       # False while accumulating (DDP no_sync, misc.py:144-148)
         target = int(bucket_mb * 1024 * 1024 / 4)
+        tail_mb = float(os.environ.get("DAVF_TAIL_BUCKET_MB", bucket_mb if tail_mb is None else tail_mb))
+        tail = max(1, min(target, int(tail_mb * 1024 * 1024 / 4)))
         n = len(store.params)
-        # buckets of parameter indices, cut from the end of the buffer
+        # buckets of parameter indices, cut from the end of the buffer (the order backward produces them in).  ``tail_mb``
+        # (default: same as bucket_mb) cuts the last two buckets' worth -- the first layers, whose gradients arrive when
+        # nothing is left to hide an exchange under -- finer; measured at N = 8 it did not pay (17.05 vs 16.74 ms: the
+        # extra NVLS launches cost more than the shorter tail saves), so it is off.
         self.buckets: List[List[int]] = []
         cur: List[int] = []
         size = 0
@@ -103,7 +114,7 @@ class GradSync:
             b, e = store.span(k)
             cur.append(k)
             size += e - b
-            if size >= target and b % ALIGN == 0:      # (a stacked k / v pair may start off the grid: never cut there)
+            if size >= (tail if b < 2 * target else target) and b % ALIGN == 0:      # (a stacked k / v pair may start off the grid: never cut there)
                 self.buckets.append(cur)
                 cur, size = [], 0
         if cur:
