@@ -293,3 +293,59 @@ def _checkpoint_resume_case(device, tmp_path):
 def test_checkpoint_manager_resume(monkeypatch, tmp_path):
     cpu_kernels.install(monkeypatch)
     _checkpoint_resume_case("cpu", tmp_path)
+
+
+def test_rehome_grads_keeps_training_identical(monkeypatch):
+    """ParamStore.rehome_grads (used to move flat_g into NCCL-registered memory) re-points every gradient view: accumulated
+    gradients survive the move and the following steps equal those of a store that never moved."""
+    cpu_kernels.install(monkeypatch)
+    from deepavfusion_b200.util.misc import Trainer
+    cfg = U.tiny_cfg()
+    image, audio = U.make_inputs(cfg, 2)
+    ni, na = U.make_noise(cfg, 2)
+    res = {}
+    for move in (False, True):
+        model = U.build_model(cfg); model.load_state_dict(O.build_state(cfg, seed=0))
+        tr = Trainer(model, optimizer=torch.optim.AdamW(_groups(model), lr=1e-3, betas=(0.9, 0.95)), accum_iter=2)
+        for it in range(4):
+            with U.inject_rand([ni, na]):
+                li, la, _, _ = model(image, audio)
+            norm, _ = tr.step(li + la)
+            if move and it == 0:                          # mid-accumulation: the half-summed gradients must come along
+                old = tr.store.flat_g
+                tr.store.rehome_grads(torch.empty_like(old))
+                assert tr.store.flat_g.data_ptr() != old.data_ptr() and torch.equal(tr.store.flat_g, old)
+                for k, p in enumerate(tr.store.params):
+                    if p.requires_grad:
+                        assert p.grad.data_ptr() == tr.store.flat_g[tr.store.offsets[k]:].data_ptr()
+                old.fill_(float("nan"))                   # nothing may read the old buffer any more
+        res[move] = (tr.store.flat_p.clone(), float(norm))
+    assert torch.equal(res[True][0], res[False][0]) and res[True][1] == res[False][1]
+
+
+def test_bucket_layout_and_registration_fallback(monkeypatch):
+    """GradSync buckets tile [0, numel) from the end on ALIGN boundaries for any bucket / tail size, and the NCCL-registered
+    gradient buffer quietly reports why it is unavailable (off by default; no NCCL process group on CPU)."""
+    cpu_kernels.install(monkeypatch)
+    from deepavfusion_b200.models.layers import ensure_store
+    from deepavfusion_b200.params import ALIGN
+    from deepavfusion_b200.util import distributed as D
+    model = U.build_model(U.tiny_cfg())
+    store = ensure_store(model)
+    for bucket_mb, tail_mb in ((0.25, None), (0.25, 0.03), (64.0, 16.0), (0.05, 0.05)):
+        sync = D.GradSync(store, bucket_mb=bucket_mb, tail_mb=tail_mb)
+        ranges = sorted(sync.ranges)
+        assert ranges[0][0] == 0 and max(hi for _, hi in ranges) == store.numel
+        for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
+            assert hi <= lo2 and lo % ALIGN == 0 and lo2 % ALIGN == 0       # disjoint, on the grid (gaps are alignment padding)
+        assert sorted(k for ks in sync.buckets for k in ks) == list(range(len(store.params)))
+        assert sync.ranges[0][1] == store.numel                              # bucket 0 is the END of the buffer (first out of backward)
+    fine = D.GradSync(store, bucket_mb=0.25, tail_mb=0.03)
+    coarse = D.GradSync(store, bucket_mb=0.25)
+    assert len(fine.buckets) > len(coarse.buckets)
+    store.sync = None
+    buf, why = D.nccl_registered_zeros(1024, "cpu")
+    assert buf is None and "DAVF_NCCL_REGISTER" in why
+    monkeypatch.setenv("DAVF_NCCL_REGISTER", "1")
+    buf, why = D.nccl_registered_zeros(1024, "cpu")
+    assert buf is None and "NCCL" in why
