@@ -13,7 +13,7 @@ all-reduce + fused AdamW (which also divides by accum_iter * world and zeroes th
 Data-parallel runs capture the bucketed gradient all-reduce too (``overlap_comm``, the default): every bucket's
 NCCL call is recorded on the communication stream at the point of backward where its last gradient has been
 produced, so in the replayed graph the all-reduce of the decoder / late-encoder buckets runs under the rest of
-backward, and the fused AdamW node follows the last bucket.  NCCL needs its communicator and internal stream
+backward, and each bucket's fused AdamW range launch follows its all-reduce on a third stream.  NCCL needs its communicator and internal stream
 to exist before capture: the eager warm-up steps run the identical bucketed path.  ``DAVF_GRAPH_NCCL=0`` (or
 ``overlap_comm=False``) falls back to capturing forward + backward only, with one all-reduce over the flat
 gradient buffer and the AdamW launch issued after the replay.
